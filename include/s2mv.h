@@ -1,0 +1,184 @@
+/*
+ * s2mv.h — C ABI of the B200-native stereo -> multiview frame pipeline.
+ *
+ * Drop-in boundary for the hot path of moddyz/stereo-to-multiview-cuda:
+ * everything `adcensus_stm` (reference d_io.cu:7-238, d_io.h:32-40) executes,
+ * plus the per-stage host-pointer entry points the reference's image driver
+ * calls (image_io.cpp:171-292).  Plain pointers and sizes only; every
+ * function returns an s2mv_status (0 = OK).  The reference's own C++ symbols
+ * (`adcensus_stm`, `ci_adcensus`, `ca_cross`, ...) are exported by the same
+ * library as one-line shims over this ABI (include/s2mv_compat.h), so
+ * video_io.cpp / image_io.cpp link unchanged.
+ *
+ * Layout conventions are the reference's: images are tightly packed
+ * interleaved BGR, `elem_sz` (= 3) bytes per pixel; cost volumes at this
+ * boundary are tables of `num_disp` plane pointers, each plane
+ * num_rows*num_cols floats; cross arms are tables of 4 plane pointers in the
+ * order UP, DOWN, LEFT, RIGHT (d_ca_cross.cu:9-15).
+ *
+ * There is no CPU fallback: every entry point fails with
+ * S2MV_ERR_NO_DEVICE / S2MV_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef S2MV_H
+#define S2MV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    S2MV_OK = 0,
+    S2MV_ERR_NO_DEVICE = 1,   /* no CUDA device / wrong architecture           */
+    S2MV_ERR_CUDA = 2,        /* a CUDA runtime call or kernel launch failed    */
+    S2MV_ERR_BAD_PARAM = 3,   /* sizes / parameters outside the supported range */
+    S2MV_ERR_NOT_CONFIGURED = 4,
+    S2MV_ERR_OOM = 5
+} s2mv_status;
+
+/* Parameters of adcensus_stm (d_io.h:32-40) plus the constants the reference
+ * hard-codes at its call sites (d_io.cu:147-151, d_dibr_bwarp.cu:63).
+ * s2mv_default_params() fills the latter with the video path's values. */
+typedef struct {
+    int num_rows, num_cols;         /* one view                                 */
+    int num_rows_out, num_cols_out; /* interlaced frame                         */
+    int elem_sz;                    /* bytes per pixel, must be 3               */
+    int num_views, angle;           /* angle in whole degrees (d_io.h:36)       */
+    int num_disp, zero_disp;
+    float ad_coeff, census_coeff;
+    float ucd, lcd;
+    int usd, lsd;
+    int thresh_s;
+    float thresh_h;
+    int irv_iterations;             /* 5   d_io.cu:147                          */
+    int bilateral_radius;           /* 7   d_io.cu:150                          */
+    float bilateral_sigma_color;    /* 5                                        */
+    float bilateral_sigma_spatial;  /* 10                                       */
+    int mask_blur_radius;           /* 10  d_dibr_bwarp.cu:63                   */
+    float mask_blur_sigma;          /* 15                                       */
+} s2mv_params;
+
+typedef struct s2mv_ctx s2mv_ctx;
+
+const char *s2mv_status_string(int status);
+const char *s2mv_last_error(void);  /* thread-local detail of the last failure */
+void s2mv_default_params(s2mv_params *p);
+
+/* Context = one GPU, one stream, one arena sized by s2mv_configure().  */
+int s2mv_create(s2mv_ctx **ctx, int device);
+void s2mv_destroy(s2mv_ctx *ctx);
+int s2mv_configure(s2mv_ctx *ctx, const s2mv_params *p);
+size_t s2mv_arena_bytes(const s2mv_ctx *ctx);
+int s2mv_device_sm_count(const s2mv_ctx *ctx);
+
+/* ---- frame entry points (replace adcensus_stm, d_io.cu:7-238) ---------- */
+
+/* Host buffers in, host buffers out; synchronous (returns after the D2H
+ * copies), exactly the contract of adcensus_stm.  `img_sbs` is
+ * num_rows x num_cols_sbs x elem_sz; left view = columns [0,num_cols),
+ * right view = [num_cols, 2*num_cols).  Outputs may be NULL to skip them. */
+int s2mv_process_sbs(s2mv_ctx *ctx, const uint8_t *img_sbs, int num_cols_sbs,
+                     float *disp_l, float *disp_r, uint8_t *interlaced);
+
+/* Same work on DEVICE pointers, enqueued on `stream` (a cudaStream_t; NULL =
+ * the context's own stream) without synchronising. */
+int s2mv_process_sbs_device(s2mv_ctx *ctx, const uint8_t *d_img_sbs, int num_cols_sbs,
+                            float *d_disp_l, float *d_disp_r, uint8_t *d_interlaced, void *stream);
+
+/* Cost-volume leg only: cost initialisation + 4-pass cross aggregation + WTA,
+ * both views (the MDE/s metric; BASELINE config 5).  Device pointers. */
+int s2mv_costvol_device(s2mv_ctx *ctx, const uint8_t *d_img_sbs, int num_cols_sbs,
+                        float *d_disp_l, float *d_disp_r, void *stream);
+
+int s2mv_synchronize(s2mv_ctx *ctx);
+
+/* Device-event timing of the last s2mv_process_sbs* call, in milliseconds:
+ * [0] prepare (demux, gray, census, arms)  [1] cost volume (CI+CA+WTA)
+ * [2] refinement (DCC, IRV, bilateral)     [3] DIBR + interlace
+ * Valid after s2mv_synchronize(); returns S2MV_ERR_BAD_PARAM if timing was
+ * not enabled with s2mv_enable_timing(ctx, 1). */
+int s2mv_enable_timing(s2mv_ctx *ctx, int on);
+int s2mv_last_timings(s2mv_ctx *ctx, float ms[4]);
+/* number of kernels the last frame call launched */
+int s2mv_last_launch_count(const s2mv_ctx *ctx);
+
+/* The two exponential tables of the combine step, as the GPU computes them
+ * (1 - ex2.approx((-c/coeff)*log2e), d_ci_adcensus.cu:27-31): 766 floats
+ * indexed by |dB|+|dG|+|dR| and 65 floats indexed by Hamming distance. */
+int s2mv_get_exp_tables(s2mv_ctx *ctx, float ad_coeff, float census_coeff,
+                        float *lut_ad_766, float *lut_cen_65);
+
+/* Taps on the last frame processed by this context (host destinations, any
+ * may be NULL): WTA disparities, cross-check outliers, post-IRV disparities,
+ * packed arms (4 planes each), occlusion masks, the num_views synthesised
+ * views.  For parity tests; s2mv_enable_taps(ctx, 1) must precede the frame
+ * (it adds a few device-to-device copies per frame, so it is off by default). */
+int s2mv_enable_taps(s2mv_ctx *ctx, int on);
+int s2mv_read_taps(s2mv_ctx *ctx, float *wta_l, float *wta_r,
+                   uint8_t *outliers_l, uint8_t *outliers_r,
+                   float *irv_l, float *irv_r,
+                   uint8_t *arms_l, uint8_t *arms_r,
+                   float *mask_l, float *mask_r, uint8_t *views);
+
+/* ---- per-stage entry points, HOST pointers (image_io.cpp:171-292) ------
+ * Each one uploads, runs the same kernels the frame path uses, downloads;
+ * they create a transient context on device 0 when `ctx` is NULL. */
+
+/* d_ci_adcensus.cu:188-378 */
+int s2mv_ci_adcensus(s2mv_ctx *ctx, const uint8_t *img_l, const uint8_t *img_r,
+                     float **cost_l, float **cost_r, float ad_coeff, float census_coeff,
+                     int num_disp, int zero_disp, int num_rows, int num_cols, int elem_sz);
+/* building blocks of the above, exposed for bit-exact integer parity:
+ * gray (d_mux_common.cu:7-21), 48-bit census (d_ci_census.cu:18-50),
+ * AD cost (d_ci_ad.cu:73-159), Hamming cost (d_ci_census.cu:197-254) */
+int s2mv_gray(s2mv_ctx *ctx, const uint8_t *img, uint8_t *gray, int num_rows, int num_cols, int elem_sz);
+int s2mv_census(s2mv_ctx *ctx, const uint8_t *gray, uint64_t *census, int num_rows, int num_cols);
+int s2mv_ci_ad(s2mv_ctx *ctx, const uint8_t *img_l, const uint8_t *img_r, float **cost_l, float **cost_r,
+               int num_disp, int zero_disp, int num_rows, int num_cols, int elem_sz);
+int s2mv_ci_census(s2mv_ctx *ctx, const uint8_t *img_l, const uint8_t *img_r, float **cost_l, float **cost_r,
+                   int num_disp, int zero_disp, int num_rows, int num_cols, int elem_sz);
+/* d_ca_cross.cu:275-444: arms out (4 planes), cost in, aggregated cost out */
+int s2mv_ca_cross(s2mv_ctx *ctx, const uint8_t *img, uint8_t **cross, float **cost, float **acost,
+                  float ucd, float lcd, int usd, int lsd,
+                  int num_disp, int num_rows, int num_cols, int elem_sz);
+/* d_dc_wta.cu:61-122 */
+int s2mv_dc_wta(s2mv_ctx *ctx, float **cost, float *disp, int num_disp, int zero_disp,
+                int num_rows, int num_cols);
+/* d_dr_dcc.cu:130-205 */
+int s2mv_dr_dcc(s2mv_ctx *ctx, uint8_t *outliers_l, uint8_t *outliers_r,
+                const float *disp_l, const float *disp_r, int num_rows, int num_cols);
+/* d_dr_irv.cu:272-366 when host_variant != 0 (one vote pass), d_dr_irv.cu:222-269 otherwise */
+int s2mv_dr_irv(s2mv_ctx *ctx, float *disp, uint8_t *outliers, uint8_t **cross,
+                int thresh_s, float thresh_h, int num_rows, int num_cols,
+                int num_disp, int zero_disp, int usd, int iterations, int host_variant);
+/* d_filter_bilateral.cu:570-632 */
+int s2mv_filter_bilateral_1(s2mv_ctx *ctx, float *img, int radius, float sigma_color, float sigma_spatial,
+                            int num_rows, int num_cols, int num_disp);
+/* d_dibr_occl.cu:161-220 */
+int s2mv_dibr_occl(s2mv_ctx *ctx, uint8_t *occl_l, uint8_t *occl_r,
+                   const float *disp_l, const float *disp_r, int num_rows, int num_cols);
+/* d_filter.cu:169-206 */
+int s2mv_filter_bleed_1(s2mv_ctx *ctx, uint8_t *img, int radius, int num_rows, int num_cols);
+/* d_dibr_occl.cu:33-112 */
+int s2mv_dibr_occl_to_mask(s2mv_ctx *ctx, float *mask_l, float *mask_r,
+                           const uint8_t *occl_l, const uint8_t *occl_r, int num_rows, int num_cols);
+/* d_filter_gaussian.cu:173-235 (out = max(v, blur v)) */
+int s2mv_filter_gaussian_1(s2mv_ctx *ctx, float *img, int radius, float sigma_spatial,
+                           int num_rows, int num_cols);
+/* d_dibr_bwarp.cu:75-183 when blur_radius/sigma = 7/10; the frame path uses 10/15 */
+int s2mv_dibr_dbm(s2mv_ctx *ctx, uint8_t *img_out, const uint8_t *img_in_l, const uint8_t *img_in_r,
+                  const float *disp_l, const float *disp_r, const float *mask_l, const float *mask_r,
+                  float shift, int blur_radius, float blur_sigma,
+                  int num_rows, int num_cols, int elem_sz);
+/* d_mux_multiview.cu:155-222; kernel_variant 0 = choose as the reference does
+ * (kernel 2 when num_rows_out % num_views == 0, else kernel 1) */
+int s2mv_mux_multiview(s2mv_ctx *ctx, uint8_t **views, uint8_t *out, int num_views, float angle,
+                       int num_rows_in, int num_cols_in, int num_rows_out, int num_cols_out,
+                       int elem_sz, int kernel_variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2MV_H */

@@ -1,0 +1,48 @@
+#!/usr/bin/env bash
+# build_ref.sh — compile the UNMODIFIED reference device code for sm_100 into
+# oracle/_ref/libs2mv_ref.so (git-ignored; travels to the GPU box with gpurun).
+#
+# TEST INFRASTRUCTURE ONLY.  Sources are compiled where they lie under
+# $REF (default /root/reference); nothing is copied into the repository.
+# The reference's own build (makefile: -arch=sm_30, OpenCV host drivers) is
+# not used.  Three mechanical accommodations, none touching kernel bodies on
+# the hot path:
+#   1. --expt-relaxed-constexpr  (d_mux_multiview.cu:57-58 calls fmax(float,int))
+#   2. d_filter_bilateral.cu:41-220 (dead texture-reference variants, API
+#      removed in CUDA 12) is dropped from a scratch copy under $TMPDIR
+#   3. empty stub headers for the two OpenCV includes of d_io.h:9-10
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${REF:-/root/reference}"
+OUT="$HERE/_ref"
+if [ ! -d "$REF" ]; then
+    echo "build_ref: $REF not present (GPU box?) — keeping prebuilt $OUT" >&2
+    exit 0
+fi
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+TMP="$(mktemp -d)"
+trap 'rm -rf "$TMP"' EXIT
+mkdir -p "$OUT" "$TMP/stubs/opencv2/core" "$TMP/obj"
+: > "$TMP/stubs/opencv2/core/core.hpp"
+: > "$TMP/stubs/opencv2/opencv.hpp"
+sed '41,220d' "$REF/d_filter_bilateral.cu" > "$TMP/d_filter_bilateral.cu"
+
+FLAGS=(-O3 -gencode arch=compute_100,code=sm_100 -dc --expt-relaxed-constexpr -w
+       -Xcompiler -fPIC -I "$TMP/stubs" -I "$REF")
+# makefile:20 DEVICE_OBJECTS
+UNITS=(d_io d_alu d_ci_census d_ci_ad d_mux_multiview d_tx_scale d_ci_adcensus d_ca_cross_sum
+       d_ca_cross d_dc_wta d_dibr_fwarp d_dibr_bwarp d_dibr_occl d_mux_common d_dc_hslo
+       d_demux_common d_filter d_filter_gaussian d_op d_dr_dcc d_dr_irv)
+pids=()
+for u in "${UNITS[@]}"; do
+    "$NVCC" "${FLAGS[@]}" "$REF/$u.cu" -o "$TMP/obj/$u.o" &
+    pids+=($!)
+done
+"$NVCC" "${FLAGS[@]}" "$TMP/d_filter_bilateral.cu" -o "$TMP/obj/d_filter_bilateral.o" &
+pids+=($!)
+"$NVCC" "${FLAGS[@]}" "$HERE/ref_harness.cu" -o "$TMP/obj/ref_harness.o" &
+pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+"$NVCC" -gencode arch=compute_100,code=sm_100 -shared -Xcompiler -fPIC "$TMP"/obj/*.o \
+    -o "$OUT/libs2mv_ref.so" -lcudart
+echo "build_ref: wrote $OUT/libs2mv_ref.so"

@@ -1,0 +1,197 @@
+// kernels_dibr.cuh — depth-image-based rendering: coverage maps, mask
+// dilation, backward warps + blend for the intermediate views, and the
+// slanted-lenticular interlace.
+#pragma once
+#include "common.cuh"
+
+namespace s2mv {
+
+// dibr_find_occlusion_kernel for both directions (d_dibr_occl.cu:114-159):
+// occl_r[x + trunc(disp_l)] = 1, occl_l[x + trunc(-disp_r)] = 1 ("1" = covered).
+// Both maps must be zeroed first.  All writers store 1: order-free.
+__global__ void __launch_bounds__(256)
+k_occl(const float *__restrict__ dispL, const float *__restrict__ dispR, uint8_t *__restrict__ occlL,
+       uint8_t *__restrict__ occlR, int H, int W)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    const size_t row = (size_t)y * W;
+    int sd = (int)__fmul_rn(dispL[row + x], 1.0f);
+    occlR[row + clampi(x + sd, 0, W - 1)] = 1;
+    sd = (int)__fmul_rn(dispR[row + x], -1.0f);
+    occlL[row + clampi(x + sd, 0, W - 1)] = 1;
+}
+
+// filter_bleed_1_kernel (d_filter.cu:105-139) and, optionally fused,
+// dibr_occl_to_mask_kernel (d_dibr_occl.cu:17-31).
+__global__ void __launch_bounds__(256)
+k_bleed(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, float *__restrict__ mask, int radius,
+        int H, int W)
+{
+    int tx = blockIdx.x * blockDim.x + threadIdx.x;
+    int ty = blockIdx.y;
+    if (tx >= W) return;
+    const int kernel_sz = (2 * radius + 1) * (2 * radius + 1);
+    int count = 0;
+    for (int y = -radius; y <= radius; ++y)
+        for (int x = -radius; x <= radius; ++x) {
+            int sx = tx + x, sy = ty + y;
+            if (sx < 0) sx = -sx;
+            if (sy < 0) sy = -sy;
+            if (sx > W - 1) sx = W - 1 - x;
+            if (sy > H - 1) sy = H - 1 - y;
+            if (in[(size_t)sy * W + sx] > 0) ++count;
+        }
+    const uint8_t a = in[(size_t)ty * W + tx];
+    const uint8_t r = ((double)count > (kernel_sz - 1) * 0.30) ? (uint8_t)1 : a;
+    out[(size_t)ty * W + tx] = r;
+    if (mask) mask[(size_t)ty * W + tx] = (r == 1) ? 1.0f : 0.0f;
+}
+
+__global__ void k_occl_to_mask(const uint8_t *__restrict__ occl, float *__restrict__ mask, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mask[i] = occl[i] == 1 ? 1.0f : 0.0f;
+}
+
+// filter_gaussian_1_kernel_1 (d_filter_gaussian.cu:9-88): out = max(v, blur(v)),
+// with op_invertnormf_kernel (d_op.cu:7-16) optionally folded into the tile load.
+constexpr int kGaW = 32, kGaH = 8;
+
+__global__ void __launch_bounds__(kGaW *kGaH)
+k_gauss_dilate(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ kernel,
+               int radius, int invert, int H, int W)
+{
+    extern __shared__ float gsm[];
+    const int tw = kGaW + 2 * radius, th = kGaH + 2 * radius, kw = 2 * radius + 1;
+    float *tile = gsm, *sk = tile + tw * th;
+    const int tid = threadIdx.y * kGaW + threadIdx.x, nt = kGaW * kGaH;
+    const int bx = blockIdx.x * kGaW, by = blockIdx.y * kGaH;
+    for (int i = tid; i < tw * th; i += nt) {
+        int ty = i / tw, tx = i - ty * tw;
+        float v = in[(size_t)clampi(by + ty - radius, 0, H - 1) * W + clampi(bx + tx - radius, 0, W - 1)];
+        tile[i] = invert ? __fsub_rn(1.0f, v) : v;
+    }
+    for (int i = tid; i < kw * kw; i += nt) sk[i] = kernel[i];
+    __syncthreads();
+    const int gx = bx + threadIdx.x, gy = by + threadIdx.y;
+    if (gx >= W || gy >= H) return;
+    const float va = tile[(threadIdx.y + radius) * tw + threadIdx.x + radius];
+    float res = 0.0f, norm = 0.0f;
+    for (int y = 0; y < kw; ++y) {
+        const float *trow = tile + (threadIdx.y + y) * tw + threadIdx.x;
+        const float *krow = sk + y * kw;
+        for (int x = 0; x < kw; ++x) {
+            const float w = krow[x];
+            norm = __fadd_rn(norm, w);
+            res = __fmaf_rn(trow[x], w, res);
+        }
+    }
+    const float q = __fdiv_rn(res, norm);
+    out[(size_t)gy * W + gx] = (va < q) ? q : va;
+}
+
+// One intermediate view per blockIdx.z: the two backward warps
+// (dibr_backward_warp_kernel, d_dibr_bwarp.cu:5-22) and the blend
+// (mux_merge_AB_kernel, d_mux_common.cu:23-46) of d_dibr_dbm, fused.
+// `tmask` is the dilated inverse of mask_r, which does not depend on the view,
+// so it is computed once per frame instead of once per view (d_dibr_bwarp.cu:60-63).
+struct DbmArgs {
+    const uint32_t *pixL, *pixR;
+    const float *dispL, *dispR, *maskL, *maskR, *tmask;
+    uint8_t *views;      // [num_views][H][W][3]
+    float shift[16];     // per intermediate view
+    int view_index[16];
+    int H, W;
+};
+
+__device__ __forceinline__ uint32_t warp_fetch(const uint32_t *__restrict__ pixrow, float disp, float shift, int tx, int W)
+{
+    // PTX of the reference: fma.rn(shift, disp, (float)tx); max 0; min W-1; cvt.rzi
+    float fx = __fmaf_rn(shift, disp, (float)tx);
+    fx = fminf(fmaxf(fx, 0.0f), (float)(W - 1));
+    return pixrow[(int)fx];  // bilinear at integral coordinates = plain fetch (Q23)
+}
+
+__global__ void __launch_bounds__(256)
+k_dbm(const DbmArgs a)
+{
+    int tx = blockIdx.x * blockDim.x + threadIdx.x;
+    int ty = blockIdx.y;
+    if (tx >= a.W) return;
+    const int vi = blockIdx.z;
+    const float shift = a.shift[vi];
+    const size_t row = (size_t)ty * a.W, i = row + tx;
+    const float mr = a.maskR[i], ml = a.maskL[i], m = a.tmask[i];
+    const uint32_t pl = warp_fetch(a.pixL + row, a.dispR[i], -shift, tx, a.W);
+    const uint32_t pr = warp_fetch(a.pixR + row, a.dispL[i], (float)(1.0 - (double)shift), tx, a.W);
+    const float im = __fsub_rn(1.0f, m);
+    uint8_t *o = a.views + ((size_t)a.view_index[vi] * a.H * a.W + i) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float cl = (float)((pl >> (8 * c)) & 0xff), cr = (float)((pr >> (8 * c)) & 0xff);
+        const uint32_t wl = __float2uint_rz(__fmul_rn(cl, mr)) & 0xff;  // warped left, masked by mask_r
+        const uint32_t wr = __float2uint_rz(__fmul_rn(cr, ml)) & 0xff;  // warped right, masked by mask_l
+        const uint32_t b = __float2uint_rz(__fmul_rn(im, (float)wl)) & 0xff;
+        const uint32_t q = __float2uint_rz(__fmul_rn(m, (float)wr)) & 0xff;
+        o[c] = (uint8_t)(b + q);
+    }
+}
+
+// mux_multiview_kernel_2 / mux_multiview_kernel (d_mux_multiview.cu:38-124)
+struct MuxArgs {
+    const uint8_t *views[16];
+    uint8_t *out;
+    int num_views, Hin, Win, Hout, Wout, variant;
+    float y_interval, inv_y_interval;
+    int rint_y;  // (int)roundf(y_interval)
+};
+
+__device__ __forceinline__ uint8_t bilinear_u8(const uint8_t *__restrict__ data, int off, int x0, int x1, int y0,
+                                                int y1, float wx, float wy, int W)
+{
+    // fast_bilinear_interp (d_mux_multiview.cu:10-36) with the PTX's fma placement
+    const float v00 = (float)data[((size_t)y0 * W + x0) * 3 + off], v01 = (float)data[((size_t)y0 * W + x1) * 3 + off];
+    const float v10 = (float)data[((size_t)y1 * W + x0) * 3 + off], v11 = (float)data[((size_t)y1 * W + x1) * 3 + off];
+    const float iwx = __fsub_rn(1.0f, wx), iwy = __fsub_rn(1.0f, wy);
+    const float top = __fmaf_rn(iwx, v00, __fmul_rn(wx, v01));
+    const float bot = __fmaf_rn(iwx, v10, __fmul_rn(wx, v11));
+    return (uint8_t)__float2uint_rz(__fmaf_rn(iwy, top, __fmul_rn(wy, bot)));
+}
+
+__global__ void __launch_bounds__(256)
+k_mux(const MuxArgs a)
+{
+    int tx = blockIdx.x * blockDim.x + threadIdx.x;
+    int ty = blockIdx.y;
+    if (tx >= a.Wout) return;
+    float xs = __fmul_rn(__fdiv_rn((float)tx, (float)a.Wout), (float)a.Win);
+    float ys = __fmul_rn(__fdiv_rn((float)ty, (float)a.Hout), (float)a.Hin);
+    xs = (float)fmin(fmax((double)xs, 0.0), (double)(float)(a.Win - 1));
+    ys = (float)fmin(fmax((double)ys, 0.0), (double)(float)(a.Hin - 1));
+    const float xi = (float)a.num_views;
+    float yv;
+    if (a.variant == 2) {
+        yv = __fadd_rn((float)(ty % a.rint_y), 1.0f);
+        yv = __fmul_rn(yv, xi);
+        yv = __fmul_rn(a.inv_y_interval, yv);
+    } else {
+        yv = (float)((double)(ty % a.rint_y) + 1.0);
+        yv = __fdiv_rn(__fmul_rn(yv, xi), a.y_interval);
+    }
+    int xv = (tx * 3 + (int)yv) % ((int)xi);
+    int rv = xv < 0 ? xv + a.num_views : xv;
+    int gv = rv + 1, bv = rv + 2;
+    if (gv >= a.num_views) gv -= a.num_views;
+    if (bv >= a.num_views) bv -= a.num_views;
+    const int x0 = (int)floorf(xs), y0 = (int)floorf(ys);
+    const int x1 = min(x0 + 1, a.Win - 1), y1 = min(y0 + 1, a.Hin - 1);
+    const float wx = __fsub_rn(xs, (float)x0), wy = __fsub_rn(ys, (float)y0);
+    uint8_t *o = a.out + ((size_t)ty * a.Wout + tx) * 3;
+    o[0] = bilinear_u8(a.views[bv], 0, x0, x1, y0, y1, wx, wy, a.Win);
+    o[1] = bilinear_u8(a.views[gv], 1, x0, x1, y0, y1, wx, wy, a.Win);
+    o[2] = bilinear_u8(a.views[rv], 2, x0, x1, y0, y1, wx, wy, a.Win);
+}
+
+}  // namespace s2mv

@@ -1,0 +1,159 @@
+// kernels_prep.cuh — per-pixel preparation: SBS split, BGRx packing, gray,
+// census transform, cross arms.  All O(W*H); none of them touches the volume.
+#pragma once
+#include "common.cuh"
+
+namespace s2mv {
+
+// demux_sbs (d_demux_common.cu:8-33) + mux_average_kernel (d_mux_common.cu:7-21)
+// in one pass.  srcL/srcR are two row-pitched BGR images (for an SBS frame they
+// alias one buffer, srcR = srcL + 3*W).  Writes 32-bit BGRx pixels (one aligned
+// load per pixel for every later stage), gray, and optional packed BGR copies
+// (the outermost views of the interlace).
+__global__ void __launch_bounds__(256)
+k_unpack(const uint8_t *__restrict__ srcL, const uint8_t *__restrict__ srcR, size_t pitch,
+         uint32_t *__restrict__ pixL, uint32_t *__restrict__ pixR,
+         uint8_t *__restrict__ grayL, uint8_t *__restrict__ grayR,
+         uint8_t *__restrict__ bgrL, uint8_t *__restrict__ bgrR, int H, int W)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    const float c = 0.3333333333333f;  // 0x3EAAAAAB
+    size_t i = (size_t)y * W + x;
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+        const uint8_t *s = (v ? srcR : srcL) + (size_t)y * pitch + (size_t)x * 3;
+        uint32_t b = s[0], g = s[1], r = s[2];
+        (v ? pixR : pixL)[i] = b | (g << 8) | (r << 16);
+        // PTX of the reference: mul(g,c); fma(b,c,.); fma(r,c,.); cvt.rzi.u32; st.u8
+        float f = __fmaf_rn((float)r, c, __fmaf_rn((float)b, c, __fmul_rn((float)g, c)));
+        (v ? grayR : grayL)[i] = (uint8_t)__float2uint_rz(f);
+        uint8_t *o = v ? bgrR : bgrL;
+        if (o) {
+            o[i * 3 + 0] = (uint8_t)b;
+            o[i * 3 + 1] = (uint8_t)g;
+            o[i * 3 + 2] = (uint8_t)r;
+        }
+    }
+}
+
+// mux_average_kernel alone (stage API)
+__global__ void __launch_bounds__(256)
+k_gray(const uint8_t *__restrict__ img, uint8_t *__restrict__ gray, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float c = 0.3333333333333f;
+    float b = (float)img[i * 3], g = (float)img[i * 3 + 1], r = (float)img[i * 3 + 2];
+    float f = __fmaf_rn(r, c, __fmaf_rn(b, c, __fmul_rn(g, c)));
+    gray[i] = (uint8_t)__float2uint_rz(f);
+}
+
+// tx_census_9x7_kernel_3 (d_ci_census.cu:18-50).  FULL = the 48-bit string the
+// reference stores; !FULL = its low 32 bits, the only ones alu_hamdist_64 ever
+// sees (rows y = -1, 1, 2, 3 of the 9x7 window).
+template <bool FULL, typename OutT>
+__global__ void __launch_bounds__(256)
+k_census(const uint8_t *__restrict__ gray, OutT *__restrict__ census, int H, int W)
+{
+    int gx = blockIdx.x * blockDim.x + threadIdx.x;
+    int gy = blockIdx.y;
+    if (gx >= W) return;
+    uint8_t centre = gray[(size_t)gy * W + gx];
+    OutT c = 0;
+#pragma unroll
+    for (int y = -3; y <= 3; ++y) {
+        if (y == 0) continue;
+        if (!FULL && y < -1) continue;
+        int cy = clampi(gy + y, 0, H - 1);
+        const uint8_t *row = gray + (size_t)cy * W;
+#pragma unroll
+        for (int x = -4; x <= 4; ++x) {
+            if (x == 0) continue;
+            int cx = clampi(gx + x, 0, W - 1);
+            c = (OutT)(c << 1);
+            if (row[cx] < centre) c = c + 1;
+        }
+    }
+    census[(size_t)gy * W + gx] = c;
+}
+
+// ca_cross_construction_kernel (d_ca_cross.cu:17-172): the arm is assigned
+// before the colour test, so it ends on the first failing pixel (Q6).
+__device__ __forceinline__ int max_abs_diff3(uint32_t a, uint32_t b)
+{
+    uint32_t d = __vabsdiffu4(a, b);
+    return max(max((int)(d & 0xff), (int)((d >> 8) & 0xff)), (int)((d >> 16) & 0xff));
+}
+
+__device__ __forceinline__ int arm_walk(const uint32_t *__restrict__ pix, int x, int y, int dx, int dy,
+                                        uint32_t anchor, float ucd, float lcd, int usd, int lsd, int H, int W)
+{
+    uint32_t prev = anchor;
+    int arm = 0;
+    for (int s = 1; s <= usd; ++s) {
+        int cx = x + dx * s, cy = y + dy * s;
+        if (cx < 0 || cx > W - 1 || cy < 0 || cy > H - 1) break;
+        arm = s;
+        uint32_t c = __ldg(pix + (size_t)cy * W + cx);
+        float ac = (float)max_abs_diff3(c, anchor), cp = (float)max_abs_diff3(c, prev);
+        if (s > lsd) {
+            if (ac > ucd) break;
+        } else {
+            if (ac > lcd || cp > lcd) break;
+        }
+        prev = c;
+    }
+    return arm;
+}
+
+__global__ void __launch_bounds__(256)
+k_arms(const uint32_t *__restrict__ pix, uint32_t *__restrict__ arms, float ucd, float lcd, int usd, int lsd,
+       int H, int W)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= W) return;
+    uint32_t a = pix[(size_t)y * W + x];
+    int u = arm_walk(pix, x, y, 0, -1, a, ucd, lcd, usd, lsd, H, W);
+    int d = arm_walk(pix, x, y, 0, +1, a, ucd, lcd, usd, lsd, H, W);
+    int l = arm_walk(pix, x, y, -1, 0, a, ucd, lcd, usd, lsd, H, W);
+    int r = arm_walk(pix, x, y, +1, 0, a, ucd, lcd, usd, lsd, H, W);
+    arms[(size_t)y * W + x] = (uint32_t)u | ((uint32_t)d << 8) | ((uint32_t)l << 16) | ((uint32_t)r << 24);
+}
+
+// packed arms <-> the reference's four byte planes (UP, DOWN, LEFT, RIGHT)
+__global__ void k_arms_unpack(const uint32_t *__restrict__ arms, uint8_t *__restrict__ planes, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t a = arms[i];
+    planes[i] = a & 0xff;
+    planes[n + i] = (a >> 8) & 0xff;
+    planes[2 * n + i] = (a >> 16) & 0xff;
+    planes[3 * n + i] = a >> 24;
+}
+__global__ void k_arms_pack(const uint8_t *__restrict__ planes, uint32_t *__restrict__ arms, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    arms[i] = (uint32_t)planes[i] | ((uint32_t)planes[n + i] << 8) | ((uint32_t)planes[2 * n + i] << 16) |
+              ((uint32_t)planes[3 * n + i] << 24);
+}
+
+// Exponential tables of the combine step, built with the reference's own
+// instruction sequence so the table entries are bit-identical to what
+// ci_adcensus_kernel would compute per element.
+__global__ void k_build_luts(float inv_ad, float inv_cen, float *__restrict__ lut_ad, float *__restrict__ lut_cen)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < kAdLutSize) {
+        // ci_ad_kernel_5: (float)(|dB|+|dG|+|dR|) * 0.33333333333f  (one mul.f32)
+        float ad = __fmul_rn((float)i, 0.33333333333f);
+        lut_ad[i] = ref_one_minus_exp(ad, inv_ad);
+    }
+    if (i < kCenLutSize) lut_cen[i] = ref_one_minus_exp((float)i, inv_cen);
+}
+
+}  // namespace s2mv

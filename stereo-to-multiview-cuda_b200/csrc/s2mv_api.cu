@@ -1,0 +1,821 @@
+// s2mv_api.cu — context, arena and the C ABI of include/s2mv.h.
+//
+// The reference allocates and frees >30 device buffers (four of them multi-GB)
+// and synchronises the device ~25 times per frame (d_io.cu:43-237).  Here one
+// context owns one arena sized at configure time; a frame is a fixed sequence
+// of launches on one stream with no host synchronisation inside it.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/s2mv.h"
+#include "common.cuh"
+#include "kernels_cost.cuh"
+#include "kernels_dibr.cuh"
+#include "kernels_prep.cuh"
+#include "kernels_refine.cuh"
+
+using namespace s2mv;
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e__ = (call);                                                                         \
+        if (e__ != cudaSuccess)                                                                           \
+            return fail(e__ == cudaErrorMemoryAllocation ? S2MV_ERR_OOM : S2MV_ERR_CUDA, "%s:%d %s: %s", \
+                        __FILE__, __LINE__, #call, cudaGetErrorString(e__));                              \
+    } while (0)
+#define KCHECK() CU(cudaGetLastError())
+#define TRY(call)                     \
+    do {                              \
+        int s__ = (call);             \
+        if (s__ != S2MV_OK) return s__; \
+    } while (0)
+
+extern "C" const char *s2mv_status_string(int s)
+{
+    switch (s) {
+        case S2MV_OK: return "ok";
+        case S2MV_ERR_NO_DEVICE: return "no usable CUDA device";
+        case S2MV_ERR_CUDA: return "CUDA error";
+        case S2MV_ERR_BAD_PARAM: return "bad parameter";
+        case S2MV_ERR_NOT_CONFIGURED: return "context not configured";
+        case S2MV_ERR_OOM: return "out of device memory";
+    }
+    return "unknown";
+}
+extern "C" const char *s2mv_last_error(void) { return g_err; }
+
+extern "C" void s2mv_default_params(s2mv_params *p)
+{
+    memset(p, 0, sizeof(*p));
+    p->elem_sz = 3;
+    p->num_views = 8;
+    p->angle = 18;
+    p->num_disp = 64;
+    p->zero_disp = 32;
+    p->ad_coeff = 10.f;
+    p->census_coeff = 30.f;
+    p->ucd = 20.f;
+    p->lcd = 6.f;
+    p->usd = 17;
+    p->lsd = 9;
+    p->thresh_s = 20;
+    p->thresh_h = 0.4f;
+    p->irv_iterations = 5;          // d_io.cu:147
+    p->bilateral_radius = 7;        // d_io.cu:150
+    p->bilateral_sigma_color = 5.f;
+    p->bilateral_sigma_spatial = 10.f;
+    p->mask_blur_radius = 10;       // d_dibr_bwarp.cu:63
+    p->mask_blur_sigma = 15.f;
+}
+
+// ------------------------------------------------------ host-side weights
+#define REF_PI 3.14159265359f  // d_filter_gaussian.cu:7
+// gaussian2D / generateGaussianKernel (d_filter_gaussian.cu:237-255), same libm calls
+static void host_gaussian_kernel(std::vector<float> &k, int radius, float sigma)
+{
+    int w = 2 * radius + 1;
+    k.resize((size_t)w * w);
+    for (int y = -radius; y <= radius; ++y)
+        for (int x = -radius; x <= radius; ++x) {
+            float variance = (float)pow((double)sigma, 2.0);
+            float exponent = (float)(-(pow((double)(float)x, 2.0) + pow((double)(float)y, 2.0)) / (double)(2 * variance));
+            k[(x + radius) + (y + radius) * w] = expf(exponent) / (2 * REF_PI * variance);
+        }
+}
+// gaussian1D_host / generateGaussian1D (d_filter_bilateral.cu:26-39)
+static void host_gaussian_1d(std::vector<float> &k, int size, float sigma)
+{
+    k.resize(size > 0 ? size : 1);
+    for (int i = 0; i < size; ++i) {
+        float variance = (float)pow((double)sigma, 2.0);
+        float power = (float)pow((double)(float)i, 2.0);
+        float exponent = -power / (2 * variance);
+        k[i] = expf(exponent) / sqrtf(2 * REF_PI * variance);
+    }
+}
+
+// ------------------------------------------------------------ cost plan
+struct CostPlan {
+    int D, Dp, LP, LPtot, nchunks, usd, M, S_ci, S_ld;
+    size_t smem_ci, smem_ld, smem_v;
+    int nbands, rows_per_band;
+};
+
+static size_t hpass_smem(int S, int halo, int Dc, int M, bool ci)
+{
+    size_t P = (size_t)S + 2 * halo;
+    size_t b = P * Dc * sizeof(float);
+    if (ci) b += 4 * (P + 2 * (size_t)M) * sizeof(uint32_t) + (768 + 68) * sizeof(float);
+    return b;
+}
+
+static int pick_segment(int W, int halo, int Dc, int M, bool ci, int LP, size_t *smem_out)
+{
+    // widest segment whose tile leaves room for 3 CTAs per SM (<= 74 KB each),
+    // else 2 (<= 110 KB), else 1; a multiple of the pixels processed per sweep
+    const int G = kHThreads / LP;
+    const size_t budgets[3] = {74 * 1024, 110 * 1024, 220 * 1024};
+    for (int b = 0; b < 3; ++b) {
+        int S = ((W + G - 1) / G) * G;
+        if (S > 256) S = 256;
+        for (; S >= G; S -= G) {
+            size_t sm = hpass_smem(S, halo, Dc, M, ci);
+            if (sm <= budgets[b] && (S >= 4 * halo || b == 2 || S >= W)) {
+                *smem_out = sm;
+                return S;
+            }
+        }
+    }
+    return 0;
+}
+
+static int make_plan(CostPlan &pl, int H, int W, int D, int zd, int usd, int sm_count)
+{
+    if (D < 1 || zd < 0 || zd > D || usd < 0 || usd > 64) return fail(S2MV_ERR_BAD_PARAM, "num_disp/zero_disp/usd out of range");
+    pl.D = D;
+    pl.usd = usd;
+    if (D <= 128) {
+        int dp = 4;
+        while (dp < D) dp <<= 1;
+        pl.Dp = dp;
+        pl.nchunks = 1;
+        pl.LP = dp / 4;
+    } else {
+        pl.Dp = ((D + 127) / 128) * 128;
+        pl.nchunks = pl.Dp / 128;
+        pl.LP = 32;
+    }
+    pl.LPtot = pl.Dp / 4;
+    pl.M = zd > D - 1 - zd ? zd : D - 1 - zd;
+    if (pl.M < 0) pl.M = 0;
+    pl.S_ci = pick_segment(W, usd, 4 * pl.LP, pl.M, true, pl.LP, &pl.smem_ci);
+    pl.S_ld = pick_segment(W, usd, 4 * pl.LP, pl.M, false, pl.LP, &pl.smem_ld);
+    if (!pl.S_ci || !pl.S_ld) return fail(S2MV_ERR_BAD_PARAM, "tile does not fit shared memory");
+    pl.smem_v = (size_t)(2 * usd + kVPrefetch) * kVThreads * sizeof(float4);
+    if (pl.smem_v > 220 * 1024) return fail(S2MV_ERR_BAD_PARAM, "usd too large for the vertical ring");
+    // enough CTAs for ~8 waves, bands not shorter than 4*usd rows
+    long ctas_per_band = (((long)W * pl.LPtot + kVThreads - 1) / kVThreads) * 2;
+    int resident = (int)(220 * 1024 / pl.smem_v);
+    if (resident > 16) resident = 16;
+    long want = (long)sm_count * resident * 8;
+    int nb = (int)((want + ctas_per_band - 1) / ctas_per_band);
+    int maxb = H / (4 * usd > 0 ? 4 * usd : 1);
+    if (nb > maxb) nb = maxb;
+    if (nb < 1) nb = 1;
+    pl.rows_per_band = (H + nb - 1) / nb;
+    pl.nbands = (H + pl.rows_per_band - 1) / pl.rows_per_band;
+    return S2MV_OK;
+}
+
+// ------------------------------------------------------------ the context
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct s2mv_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool configured = false, timing = false, taps = false;
+    s2mv_params prm;
+    CostPlan plan;
+    size_t arena_bytes = 0;
+    std::vector<void *> allocs;
+
+    // arena
+    uint8_t *sbs = nullptr;
+    size_t sbs_bytes = 0;
+    uint32_t *pix[2] = {}, *cen[2] = {}, *arms[2] = {};
+    uint8_t *gray[2] = {};
+    float *lutAd = nullptr, *lutCen = nullptr;
+    float lut_ad_coeff = -1.f, lut_cen_coeff = -1.f;
+    float *vol[2] = {};  // ping-pong volumes, each [2 views][H][W][Dp]
+    unsigned long long *wta_key[2] = {};
+    float *disp[2] = {}, *dispF[2] = {};  // WTA/IRV disparities; bilateral output
+    uint8_t *outl[2] = {}, *disoccl[2] = {};
+    int *irv_list[2] = {}, *irv_vote[2] = {}, *irv_count = nullptr;
+    float *bil_spatial = nullptr, *bil_colour = nullptr, *gauss_kernel = nullptr;
+    uint8_t *occl[2] = {}, *occlB[2] = {};
+    float *mask[2] = {}, *tmask = nullptr;
+    uint8_t *views = nullptr, *interlaced = nullptr;
+    // taps
+    float *tap_wta[2] = {}, *tap_irv[2] = {};
+    uint8_t *tap_outl[2] = {};
+    // pinned staging for the host entry point
+    uint8_t *h_sbs = nullptr, *h_interlaced = nullptr;
+    float *h_disp[2] = {};
+    size_t h_sbs_bytes = 0;
+    // timing
+    cudaEvent_t ev[5] = {};
+    int launches = 0;
+    float y_interval = 0.f;
+};
+
+static int dev_alloc(s2mv_ctx *c, void **p, size_t bytes)
+{
+    if (bytes == 0) bytes = 16;
+    CU(cudaMalloc(p, bytes));
+    c->allocs.push_back(*p);
+    c->arena_bytes += bytes;
+    return S2MV_OK;
+}
+template <typename T>
+static int dev_alloc_t(s2mv_ctx *c, T **p, size_t count) { return dev_alloc(c, (void **)p, count * sizeof(T)); }
+
+static void free_arena(s2mv_ctx *c)
+{
+    for (void *p : c->allocs) cudaFree(p);
+    c->allocs.clear();
+    c->arena_bytes = 0;
+    if (c->h_sbs) cudaFreeHost(c->h_sbs);
+    if (c->h_interlaced) cudaFreeHost(c->h_interlaced);
+    for (int v = 0; v < 2; ++v)
+        if (c->h_disp[v]) cudaFreeHost(c->h_disp[v]);
+    c->h_sbs = c->h_interlaced = nullptr;
+    c->h_disp[0] = c->h_disp[1] = nullptr;
+    c->h_sbs_bytes = 0;
+    c->sbs = nullptr;
+    c->sbs_bytes = 0;
+    c->configured = false;
+}
+
+extern "C" int s2mv_create(s2mv_ctx **out, int device)
+{
+    if (!out) return fail(S2MV_ERR_BAD_PARAM, "null ctx pointer");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(S2MV_ERR_NO_DEVICE, "no CUDA device visible (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(S2MV_ERR_BAD_PARAM, "device %d out of range (%d visible)", device, n);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(S2MV_ERR_NO_DEVICE, "device %d is sm_%d%d; this build targets sm_100a", device, prop.major, prop.minor);
+    CU(cudaSetDevice(device));
+    s2mv_ctx *c = new s2mv_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return fail(S2MV_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    for (int i = 0; i < 5; ++i) cudaEventCreate(&c->ev[i]);
+    *out = c;
+    return S2MV_OK;
+}
+
+extern "C" void s2mv_destroy(s2mv_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_arena(c);
+    for (int i = 0; i < 5; ++i)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" size_t s2mv_arena_bytes(const s2mv_ctx *c) { return c ? c->arena_bytes : 0; }
+extern "C" int s2mv_device_sm_count(const s2mv_ctx *c) { return c ? c->sm_count : 0; }
+extern "C" int s2mv_last_launch_count(const s2mv_ctx *c) { return c ? c->launches : 0; }
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes)
+{
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return S2MV_OK;
+}
+
+static int set_kernel_attrs()
+{
+    static bool done = false;  // per process and device; cheap to repeat per context
+    (void)done;
+    const size_t big = 227 * 1024;
+    TRY(set_smem(k_hpass<1, true, true, false>, big));
+    TRY(set_smem(k_hpass<1, false, true, false>, big));
+    TRY(set_smem(k_hpass<2, false, true, false>, big));
+    TRY(set_smem(k_hpass<3, false, true, false>, big));
+    TRY(set_smem(k_hpass<0, true, true, false>, big));
+    TRY(set_smem(k_hpass<0, true, false, true>, big));
+    TRY(set_smem(k_vpass, big));
+    TRY(set_smem(k_bilateral, 160 * 1024));
+    TRY(set_smem(k_gauss_dilate, 160 * 1024));
+    TRY(set_smem(k_irv_vote, 64 * 1024));
+    return S2MV_OK;
+}
+
+static int build_luts(s2mv_ctx *c, float ad_coeff, float census_coeff, cudaStream_t st)
+{
+    if (c->lut_ad_coeff == ad_coeff && c->lut_cen_coeff == census_coeff) return S2MV_OK;
+    // d_ci_adcensus.cu:160 passes 1.0/coeff (double) through float kernel parameters
+    float inv_ad = (float)(1.0 / ad_coeff), inv_cen = (float)(1.0 / census_coeff);
+    k_build_luts<<<(kAdLutSize + 255) / 256, 256, 0, st>>>(inv_ad, inv_cen, c->lutAd, c->lutCen);
+    KCHECK();
+    c->lut_ad_coeff = ad_coeff;
+    c->lut_cen_coeff = census_coeff;
+    return S2MV_OK;
+}
+
+extern "C" int s2mv_configure(s2mv_ctx *c, const s2mv_params *p)
+{
+    if (!c || !p) return fail(S2MV_ERR_BAD_PARAM, "null argument");
+    if (p->elem_sz != 3) return fail(S2MV_ERR_BAD_PARAM, "elem_sz must be 3 (BGR), got %d", p->elem_sz);
+    if (p->num_rows < 1 || p->num_cols < 1 || p->num_rows_out < 1 || p->num_cols_out < 1)
+        return fail(S2MV_ERR_BAD_PARAM, "image sizes must be positive");
+    if (p->num_views < 2 || p->num_views > 16) return fail(S2MV_ERR_BAD_PARAM, "num_views must be in [2,16]");
+    if ((size_t)p->num_rows * p->num_cols > 0x7fffffffull / 4) return fail(S2MV_ERR_BAD_PARAM, "image too large");
+    if (p->bilateral_radius < 0 || p->bilateral_radius > 24 || p->mask_blur_radius < 0 || p->mask_blur_radius > 24)
+        return fail(S2MV_ERR_BAD_PARAM, "filter radius out of range");
+    if (p->ad_coeff == 0.f || p->census_coeff == 0.f) return fail(S2MV_ERR_BAD_PARAM, "coefficients must be non-zero");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CostPlan pl;
+    TRY(make_plan(pl, p->num_rows, p->num_cols, p->num_disp, p->zero_disp, p->usd, c->sm_count));
+    {   // interlace geometry (d_mux_multiview.cu:146): must not divide by zero later (Q27)
+        float yi = (float)((double)(float)p->num_views / tan((double)((float)p->angle * 3.1415926535f) / 180.0) / (double)(float)p->elem_sz);
+        if (!(fabsf(yi) < 1e9f) || (int)roundf(yi) == 0)
+            return fail(S2MV_ERR_BAD_PARAM, "angle %d gives a zero interlace period", p->angle);
+        c->y_interval = yi;
+    }
+    free_arena(c);
+    TRY(set_kernel_attrs());
+    c->prm = *p;
+    c->plan = pl;
+    c->lut_ad_coeff = c->lut_cen_coeff = -1.f;
+    const size_t n = (size_t)p->num_rows * p->num_cols;
+    const size_t vol_elems = 2 * n * pl.Dp;
+    for (int v = 0; v < 2; ++v) {
+        TRY(dev_alloc_t(c, &c->pix[v], n));
+        TRY(dev_alloc_t(c, &c->cen[v], n));
+        TRY(dev_alloc_t(c, &c->arms[v], n));
+        TRY(dev_alloc_t(c, &c->gray[v], n));
+        TRY(dev_alloc_t(c, &c->disp[v], n));
+        TRY(dev_alloc_t(c, &c->dispF[v], n));
+        TRY(dev_alloc_t(c, &c->outl[v], n));
+        TRY(dev_alloc_t(c, &c->disoccl[v], n));
+        TRY(dev_alloc_t(c, &c->irv_list[v], n));
+        TRY(dev_alloc_t(c, &c->irv_vote[v], n));
+        TRY(dev_alloc_t(c, &c->occl[v], n));
+        TRY(dev_alloc_t(c, &c->occlB[v], n));
+        TRY(dev_alloc_t(c, &c->mask[v], n));
+        TRY(dev_alloc_t(c, &c->tap_wta[v], n));
+        TRY(dev_alloc_t(c, &c->tap_irv[v], n));
+        TRY(dev_alloc_t(c, &c->tap_outl[v], n));
+        if (pl.nchunks > 1) TRY(dev_alloc_t(c, &c->wta_key[v], n));
+        TRY(dev_alloc_t(c, &c->vol[v], vol_elems));
+    }
+    TRY(dev_alloc_t(c, &c->irv_count, 2));
+    TRY(dev_alloc_t(c, &c->tmask, n));
+    TRY(dev_alloc_t(c, &c->lutAd, 768));
+    TRY(dev_alloc_t(c, &c->lutCen, 68));
+    TRY(dev_alloc_t(c, &c->views, (size_t)p->num_views * n * 3));
+    TRY(dev_alloc_t(c, &c->interlaced, (size_t)p->num_rows_out * p->num_cols_out * 3));
+    {
+        std::vector<float> k;
+        host_gaussian_kernel(k, p->bilateral_radius, p->bilateral_sigma_spatial);
+        TRY(dev_alloc_t(c, &c->bil_spatial, k.size()));
+        CU(cudaMemcpy(c->bil_spatial, k.data(), k.size() * sizeof(float), cudaMemcpyHostToDevice));
+        host_gaussian_1d(k, p->num_disp, p->bilateral_sigma_color);
+        TRY(dev_alloc_t(c, &c->bil_colour, k.size()));
+        CU(cudaMemcpy(c->bil_colour, k.data(), k.size() * sizeof(float), cudaMemcpyHostToDevice));
+        host_gaussian_kernel(k, p->mask_blur_radius, p->mask_blur_sigma);
+        TRY(dev_alloc_t(c, &c->gauss_kernel, k.size()));
+        CU(cudaMemcpy(c->gauss_kernel, k.data(), k.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    TRY(build_luts(c, p->ad_coeff, p->census_coeff, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->configured = true;
+    return S2MV_OK;
+}
+
+extern "C" int s2mv_enable_timing(s2mv_ctx *c, int on)
+{
+    if (!c) return fail(S2MV_ERR_BAD_PARAM, "null ctx");
+    c->timing = on != 0;
+    return S2MV_OK;
+}
+extern "C" int s2mv_enable_taps(s2mv_ctx *c, int on)
+{
+    if (!c) return fail(S2MV_ERR_BAD_PARAM, "null ctx");
+    c->taps = on != 0;
+    return S2MV_OK;
+}
+
+extern "C" int s2mv_synchronize(s2mv_ctx *c)
+{
+    if (!c) return fail(S2MV_ERR_BAD_PARAM, "null ctx");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return S2MV_OK;
+}
+
+extern "C" int s2mv_last_timings(s2mv_ctx *c, float ms[4])
+{
+    if (!c || !ms) return fail(S2MV_ERR_BAD_PARAM, "null argument");
+    if (!c->timing) return fail(S2MV_ERR_BAD_PARAM, "timing not enabled");
+    for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+    return S2MV_OK;
+}
+
+// ------------------------------------------------------- stage launchers
+struct Dims { int H, W; };
+
+static int launch_prepare(s2mv_ctx *c, const uint8_t *srcL, const uint8_t *srcR, size_t pitch, uint8_t *bgrL,
+                          uint8_t *bgrR, cudaStream_t st)
+{
+    const s2mv_params &p = c->prm;
+    const int H = p.num_rows, W = p.num_cols;
+    dim3 g((W + 255) / 256, H);
+    k_unpack<<<g, 256, 0, st>>>(srcL, srcR, pitch, c->pix[0], c->pix[1], c->gray[0], c->gray[1], bgrL, bgrR, H, W);
+    KCHECK();
+    for (int v = 0; v < 2; ++v) {
+        k_census<false, uint32_t><<<g, 256, 0, st>>>(c->gray[v], c->cen[v], H, W);
+        KCHECK();
+        k_arms<<<g, 256, 0, st>>>(c->pix[v], c->arms[v], p.ucd, p.lcd, p.usd, p.lsd, H, W);
+        KCHECK();
+    }
+    c->launches += 5;
+    return S2MV_OK;
+}
+
+static void fill_hargs(const s2mv_ctx *c, HArgs &a, int H, int W, int zd)
+{
+    const CostPlan &pl = c->plan;
+    memset(&a, 0, sizeof(a));
+    a.pixL = c->pix[0]; a.pixR = c->pix[1]; a.cenL = c->cen[0]; a.cenR = c->cen[1];
+    a.lutAd = c->lutAd; a.lutCen = c->lutCen;
+    a.H = H; a.W = W; a.D = pl.D; a.zd = zd;
+    a.LP = pl.LP; a.LPtot = pl.LPtot; a.nchunks = pl.nchunks;
+    a.halo = pl.usd; a.M = pl.M; a.view_first = 0;
+}
+
+// CI + H, V, V, H + WTA for both views: volA <- CI+H1; volB <- V(volA); volA <- V(volB); disp <- WTA(H(volA))
+static int launch_costvol(s2mv_ctx *c, float *dispL, float *dispR, cudaStream_t st)
+{
+    const s2mv_params &p = c->prm;
+    const CostPlan &pl = c->plan;
+    const int H = p.num_rows, W = p.num_cols;
+    const size_t n = (size_t)H * W, view_stride4 = n * pl.LPtot;
+    float4 *A = reinterpret_cast<float4 *>(c->vol[0]), *B = reinterpret_cast<float4 *>(c->vol[1]);
+    HArgs a;
+    fill_hargs(c, a, H, W, p.zero_disp);
+    for (int v = 0; v < 2; ++v) {
+        a.out[v] = A + v * view_stride4;
+        a.arms[v] = c->arms[v];
+    }
+    a.S = pl.S_ci;
+    dim3 g1((W + pl.S_ci - 1) / pl.S_ci, H, 2 * pl.nchunks);
+    k_hpass<1, true, true, false><<<g1, kHThreads, pl.smem_ci, st>>>(a);
+    KCHECK();
+
+    VArgs va;
+    memset(&va, 0, sizeof(va));
+    va.H = H; va.W = W; va.LPtot = pl.LPtot; va.usd = pl.usd; va.rows_per_band = pl.rows_per_band;
+    dim3 gv((unsigned)(((size_t)W * pl.LPtot + kVThreads - 1) / kVThreads), pl.nbands, 2);
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int v = 0; v < 2; ++v) {
+            va.in[v] = (pass == 0 ? A : B) + v * view_stride4;
+            va.out[v] = (pass == 0 ? B : A) + v * view_stride4;
+            va.arms[v] = c->arms[v];
+        }
+        k_vpass<<<gv, kVThreads, pl.smem_v, st>>>(va);
+        KCHECK();
+    }
+
+    fill_hargs(c, a, H, W, p.zero_disp);
+    for (int v = 0; v < 2; ++v) {
+        a.in[v] = A + v * view_stride4;
+        a.arms[v] = c->arms[v];
+        a.wta_key[v] = c->wta_key[v];
+    }
+    a.disp[0] = dispL; a.disp[1] = dispR;
+    a.S = pl.S_ld;
+    if (pl.nchunks > 1)
+        for (int v = 0; v < 2; ++v) CU(cudaMemsetAsync(c->wta_key[v], 0xff, n * sizeof(unsigned long long), st));
+    dim3 g4((W + pl.S_ld - 1) / pl.S_ld, H, 2 * pl.nchunks);
+    k_hpass<0, true, false, true><<<g4, kHThreads, pl.smem_ld, st>>>(a);
+    KCHECK();
+    c->launches += 4;
+    if (pl.nchunks > 1) {
+        k_wta_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->wta_key[0], dispL, p.zero_disp, n);
+        k_wta_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->wta_key[1], dispR, p.zero_disp, n);
+        KCHECK();
+        c->launches += 2;
+    }
+    return S2MV_OK;
+}
+
+static int launch_dcc(s2mv_ctx *c, const float *dL, const float *dR, uint8_t *oL, uint8_t *oR, int H, int W, cudaStream_t st)
+{
+    const size_t n = (size_t)H * W;
+    CU(cudaMemsetAsync(oL, 0, n, st));
+    CU(cudaMemsetAsync(oR, 0, n, st));
+    CU(cudaMemsetAsync(c->disoccl[0], 1, n, st));
+    CU(cudaMemsetAsync(c->disoccl[1], 1, n, st));
+    dim3 g((W + 255) / 256, H);
+    k_dcc<<<g, 256, 0, st>>>(dL, dR, oL, oR, c->disoccl[0], c->disoccl[1], H, W);
+    KCHECK();
+    k_dcc_merge<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(oL, oR, c->disoccl[0], c->disoccl[1], n);
+    KCHECK();
+    c->launches += 2;
+    return S2MV_OK;
+}
+
+// nviews = 1 or 2 views voted together; arrays indexed by view slot
+static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2], const uint32_t *const arms[2],
+                      int nviews, int H, int W, int D, int zd, int usd, int thresh_s, float thresh_h, int iterations,
+                      cudaStream_t st)
+{
+    const size_t n = (size_t)H * W;
+    IrvArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int v = 0; v < nviews; ++v) {
+        a.disp[v] = disp[v]; a.outliers[v] = outl[v]; a.arms[v] = arms[v];
+        a.list[v] = c->irv_list[v]; a.vote[v] = c->irv_vote[v]; a.count[v] = c->irv_count + v;
+    }
+    a.H = H; a.W = W; a.nbins = D > 65 ? D : 65; a.zd = zd; a.usd = usd; a.thresh_s = thresh_s; a.thresh_h = thresh_h;
+    const size_t hist_bytes = (size_t)kIrvWarps * a.nbins * sizeof(int);
+    if (hist_bytes > 64 * 1024) return fail(S2MV_ERR_BAD_PARAM, "num_disp too large for the voting histogram");
+    for (int it = 0; it < iterations; ++it) {
+        CU(cudaMemsetAsync(c->irv_count, 0, 2 * sizeof(int), st));
+        k_irv_compact<<<dim3((unsigned)((n + 255) / 256), nviews), 256, 0, st>>>(a);
+        KCHECK();
+        k_irv_vote<<<dim3(c->sm_count * 4, nviews), kIrvWarps * 32, hist_bytes, st>>>(a);
+        KCHECK();
+        k_irv_apply<<<dim3(c->sm_count * 2, nviews), 256, 0, st>>>(a);
+        KCHECK();
+        c->launches += 3;
+    }
+    return S2MV_OK;
+}
+
+static int launch_bilateral(s2mv_ctx *c, const float *in, float *out, const float *spatial, const float *colour,
+                            int radius, int ncolour, int H, int W, cudaStream_t st)
+{
+    const int tw = kBilW + 2 * radius, th = kBilH + 2 * radius, kw = 2 * radius + 1;
+    size_t smem = ((size_t)tw * th + (size_t)kw * kw + ncolour) * sizeof(float);
+    if (smem > 160 * 1024) return fail(S2MV_ERR_BAD_PARAM, "bilateral tile too large");
+    dim3 g((W + kBilW - 1) / kBilW, (H + kBilH - 1) / kBilH);
+    k_bilateral<<<g, dim3(kBilW, kBilH), smem, st>>>(in, out, spatial, colour, radius, ncolour, H, W);
+    KCHECK();
+    c->launches += 1;
+    return S2MV_OK;
+}
+
+static int launch_gauss(s2mv_ctx *c, const float *in, float *out, const float *kernel, int radius, int invert, int H,
+                        int W, cudaStream_t st)
+{
+    const int tw = kGaW + 2 * radius, th = kGaH + 2 * radius, kw = 2 * radius + 1;
+    size_t smem = ((size_t)tw * th + (size_t)kw * kw) * sizeof(float);
+    dim3 g((W + kGaW - 1) / kGaW, (H + kGaH - 1) / kGaH);
+    k_gauss_dilate<<<g, dim3(kGaW, kGaH), smem, st>>>(in, out, kernel, radius, invert, H, W);
+    KCHECK();
+    c->launches += 1;
+    return S2MV_OK;
+}
+
+static int launch_mux(s2mv_ctx *c, const uint8_t *const *views, uint8_t *out, int V, float angle, int Hin, int Win,
+                      int Hout, int Wout, int elem_sz, int variant, cudaStream_t st)
+{
+    MuxArgs m;
+    memset(&m, 0, sizeof(m));
+    for (int v = 0; v < V; ++v) m.views[v] = views[v];
+    m.out = out; m.num_views = V; m.Hin = Hin; m.Win = Win; m.Hout = Hout; m.Wout = Wout;
+    // d_mux_multiview.cu:146 (PI is the float literal 3.1415926535f)
+    float yi = (float)((double)(float)V / tan((double)(angle * 3.1415926535f) / 180.0) / (double)(float)elem_sz);
+    m.y_interval = yi;
+    m.inv_y_interval = 1.0f / yi;
+    m.rint_y = (int)roundf(yi);
+    if (m.rint_y == 0) return fail(S2MV_ERR_BAD_PARAM, "interlace period rounds to zero");
+    m.variant = variant ? variant : ((Hout % V == 0) ? 2 : 1);  // d_mux_multiview.cu:183-191
+    dim3 g((Wout + 255) / 256, Hout);
+    k_mux<<<g, 256, 0, st>>>(m);
+    KCHECK();
+    c->launches += 1;
+    return S2MV_OK;
+}
+
+// --------------------------------------------------------- frame pipeline
+static int run_frame(s2mv_ctx *c, const uint8_t *d_sbs, int num_cols_sbs, float *d_disp_l, float *d_disp_r,
+                     uint8_t *d_interlaced, bool costvol_only, cudaStream_t st)
+{
+    const s2mv_params &p = c->prm;
+    const int H = p.num_rows, W = p.num_cols, V = p.num_views;
+    const size_t n = (size_t)H * W;
+    if (num_cols_sbs < 2 * W) return fail(S2MV_ERR_BAD_PARAM, "num_cols_sbs (%d) < 2*num_cols (%d)", num_cols_sbs, 2 * W);
+    c->launches = 0;
+    if (c->timing) CU(cudaEventRecord(c->ev[0], st));
+    // views[0] = right image, views[V-1] = left image (d_io.cu:181-182)
+    uint8_t *view0 = c->views, *viewN = c->views + (size_t)(V - 1) * n * 3;
+    TRY(launch_prepare(c, d_sbs, d_sbs + (size_t)W * 3, (size_t)num_cols_sbs * 3, costvol_only ? nullptr : viewN,
+                       costvol_only ? nullptr : view0, st));
+    TRY(build_luts(c, p.ad_coeff, p.census_coeff, st));
+    if (c->timing) CU(cudaEventRecord(c->ev[1], st));
+
+    float *wl = costvol_only && d_disp_l ? d_disp_l : c->disp[0];
+    float *wr = costvol_only && d_disp_r ? d_disp_r : c->disp[1];
+    TRY(launch_costvol(c, wl, wr, st));
+    if (c->timing) CU(cudaEventRecord(c->ev[2], st));
+    if (costvol_only) {
+        if (c->timing) {
+            CU(cudaEventRecord(c->ev[3], st));
+            CU(cudaEventRecord(c->ev[4], st));
+        }
+        return S2MV_OK;
+    }
+    if (c->taps)
+        for (int v = 0; v < 2; ++v)
+            CU(cudaMemcpyAsync(c->tap_wta[v], c->disp[v], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+
+    // refinement: cross-check, region voting, bilateral (d_io.cu:139-151)
+    TRY(launch_dcc(c, c->disp[0], c->disp[1], c->outl[0], c->outl[1], H, W, st));
+    if (c->taps)
+        for (int v = 0; v < 2; ++v) CU(cudaMemcpyAsync(c->tap_outl[v], c->outl[v], n, cudaMemcpyDeviceToDevice, st));
+    {
+        float *disp[2] = {c->disp[0], c->disp[1]};
+        uint8_t *outl[2] = {c->outl[0], c->outl[1]};
+        const uint32_t *arms[2] = {c->arms[0], c->arms[1]};
+        TRY(launch_irv(c, disp, outl, arms, 2, H, W, p.num_disp, p.zero_disp, p.usd, p.thresh_s, p.thresh_h,
+                       p.irv_iterations, st));
+    }
+    if (c->taps)
+        for (int v = 0; v < 2; ++v)
+            CU(cudaMemcpyAsync(c->tap_irv[v], c->disp[v], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    float *fl = d_disp_l ? d_disp_l : c->dispF[0], *fr = d_disp_r ? d_disp_r : c->dispF[1];
+    TRY(launch_bilateral(c, c->disp[0], fl, c->bil_spatial, c->bil_colour, p.bilateral_radius, p.num_disp, H, W, st));
+    TRY(launch_bilateral(c, c->disp[1], fr, c->bil_spatial, c->bil_colour, p.bilateral_radius, p.num_disp, H, W, st));
+    if (c->timing) CU(cudaEventRecord(c->ev[3], st));
+
+    // DIBR (d_io.cu:160-191)
+    CU(cudaMemsetAsync(c->occl[0], 0, n, st));
+    CU(cudaMemsetAsync(c->occl[1], 0, n, st));
+    dim3 g((W + 255) / 256, H);
+    k_occl<<<g, 256, 0, st>>>(fl, fr, c->occl[0], c->occl[1], H, W);
+    KCHECK();
+    for (int v = 0; v < 2; ++v) {
+        k_bleed<<<g, 256, 0, st>>>(c->occl[v], c->occlB[v], c->mask[v], 1, H, W);
+        KCHECK();
+    }
+    c->launches += 3;
+    TRY(launch_gauss(c, c->mask[1], c->tmask, c->gauss_kernel, p.mask_blur_radius, 1, H, W, st));
+    if (V > 2) {
+        DbmArgs d;
+        memset(&d, 0, sizeof(d));
+        d.pixL = c->pix[0]; d.pixR = c->pix[1]; d.dispL = fl; d.dispR = fr;
+        d.maskL = c->mask[0]; d.maskR = c->mask[1]; d.tmask = c->tmask; d.views = c->views; d.H = H; d.W = W;
+        for (int v = 1; v < V - 1; ++v) {
+            // d_io.cu:187: float shift = 1.0 - ((1.0 * (float) v) / ((float) num_views - 1.0));
+            d.shift[v - 1] = (float)(1.0 - ((1.0 * (double)(float)v) / ((double)(float)V - 1.0)));
+            d.view_index[v - 1] = v;
+        }
+        k_dbm<<<dim3((W + 255) / 256, H, V - 2), 256, 0, st>>>(d);
+        KCHECK();
+        c->launches += 1;
+    }
+    const uint8_t *vp[16];
+    for (int v = 0; v < V; ++v) vp[v] = c->views + (size_t)v * n * 3;
+    TRY(launch_mux(c, vp, d_interlaced ? d_interlaced : c->interlaced, V, (float)p.angle, H, W, p.num_rows_out,
+                   p.num_cols_out, p.elem_sz, 2, st));
+    if (c->timing) CU(cudaEventRecord(c->ev[4], st));
+    return S2MV_OK;
+}
+
+extern "C" int s2mv_process_sbs_device(s2mv_ctx *c, const uint8_t *d_img_sbs, int num_cols_sbs, float *d_disp_l,
+                                       float *d_disp_r, uint8_t *d_interlaced, void *stream)
+{
+    if (!c || !d_img_sbs) return fail(S2MV_ERR_BAD_PARAM, "null argument");
+    if (!c->configured) return fail(S2MV_ERR_NOT_CONFIGURED, "call s2mv_configure first");
+    CU(cudaSetDevice(c->device));
+    return run_frame(c, d_img_sbs, num_cols_sbs, d_disp_l, d_disp_r, d_interlaced, false,
+                     stream ? (cudaStream_t)stream : c->stream);
+}
+
+extern "C" int s2mv_costvol_device(s2mv_ctx *c, const uint8_t *d_img_sbs, int num_cols_sbs, float *d_disp_l,
+                                   float *d_disp_r, void *stream)
+{
+    if (!c || !d_img_sbs) return fail(S2MV_ERR_BAD_PARAM, "null argument");
+    if (!c->configured) return fail(S2MV_ERR_NOT_CONFIGURED, "call s2mv_configure first");
+    CU(cudaSetDevice(c->device));
+    return run_frame(c, d_img_sbs, num_cols_sbs, d_disp_l, d_disp_r, nullptr, true,
+                     stream ? (cudaStream_t)stream : c->stream);
+}
+
+extern "C" int s2mv_process_sbs(s2mv_ctx *c, const uint8_t *img_sbs, int num_cols_sbs, float *disp_l, float *disp_r,
+                                uint8_t *interlaced)
+{
+    if (!c || !img_sbs) return fail(S2MV_ERR_BAD_PARAM, "null argument");
+    if (!c->configured) return fail(S2MV_ERR_NOT_CONFIGURED, "call s2mv_configure first");
+    CU(cudaSetDevice(c->device));
+    const s2mv_params &p = c->prm;
+    const size_t n = (size_t)p.num_rows * p.num_cols;
+    const size_t sbs_bytes = (size_t)p.num_rows * num_cols_sbs * 3;
+    const size_t out_bytes = (size_t)p.num_rows_out * p.num_cols_out * 3;
+    if (c->sbs_bytes < sbs_bytes) {
+        void *d = nullptr;
+        CU(cudaMalloc(&d, sbs_bytes));
+        c->allocs.push_back(d);
+        c->arena_bytes += sbs_bytes;
+        c->sbs = (uint8_t *)d;
+        c->sbs_bytes = sbs_bytes;
+    }
+    // Pageable caller buffers (cv::Mat::data in video_io.cpp:139-146) are staged through
+    // pinned memory so the copies run at full PCIe/NVLink-C2C rate and overlap nothing else.
+    if (c->h_sbs_bytes < sbs_bytes) {
+        if (c->h_sbs) cudaFreeHost(c->h_sbs);
+        CU(cudaMallocHost((void **)&c->h_sbs, sbs_bytes));
+        c->h_sbs_bytes = sbs_bytes;
+    }
+    if (!c->h_interlaced) CU(cudaMallocHost((void **)&c->h_interlaced, out_bytes));
+    for (int v = 0; v < 2; ++v)
+        if (!c->h_disp[v]) CU(cudaMallocHost((void **)&c->h_disp[v], n * sizeof(float)));
+    cudaStream_t st = c->stream;
+    cudaPointerAttributes attr;
+    bool pinned_in = cudaPointerGetAttributes(&attr, img_sbs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned_in) {
+        CU(cudaMemcpyAsync(c->sbs, img_sbs, sbs_bytes, cudaMemcpyHostToDevice, st));
+    } else {
+        memcpy(c->h_sbs, img_sbs, sbs_bytes);
+        CU(cudaMemcpyAsync(c->sbs, c->h_sbs, sbs_bytes, cudaMemcpyHostToDevice, st));
+    }
+    TRY(run_frame(c, c->sbs, num_cols_sbs, c->dispF[0], c->dispF[1], c->interlaced, false, st));
+    if (disp_l) CU(cudaMemcpyAsync(c->h_disp[0], c->dispF[0], n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (disp_r) CU(cudaMemcpyAsync(c->h_disp[1], c->dispF[1], n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (interlaced) CU(cudaMemcpyAsync(c->h_interlaced, c->interlaced, out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (disp_l) memcpy(disp_l, c->h_disp[0], n * sizeof(float));
+    if (disp_r) memcpy(disp_r, c->h_disp[1], n * sizeof(float));
+    if (interlaced) memcpy(interlaced, c->h_interlaced, out_bytes);
+    return S2MV_OK;
+}
+
+extern "C" int s2mv_get_exp_tables(s2mv_ctx *c, float ad_coeff, float census_coeff, float *lut_ad, float *lut_cen)
+{
+    if (!c || !lut_ad || !lut_cen) return fail(S2MV_ERR_BAD_PARAM, "null argument");
+    CU(cudaSetDevice(c->device));
+    float *d = nullptr;
+    CU(cudaMalloc((void **)&d, (768 + 68) * sizeof(float)));
+    float inv_ad = (float)(1.0 / ad_coeff), inv_cen = (float)(1.0 / census_coeff);
+    k_build_luts<<<(kAdLutSize + 255) / 256, 256, 0, c->stream>>>(inv_ad, inv_cen, d, d + 768);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(lut_ad, d, kAdLutSize * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(lut_cen, d + 768, kCenLutSize * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(S2MV_ERR_CUDA, "exp tables: %s", cudaGetErrorString(e));
+    return S2MV_OK;
+}
+
+extern "C" int s2mv_read_taps(s2mv_ctx *c, float *wta_l, float *wta_r, uint8_t *outliers_l, uint8_t *outliers_r,
+                              float *irv_l, float *irv_r, uint8_t *arms_l, uint8_t *arms_r, float *mask_l,
+                              float *mask_r, uint8_t *views)
+{
+    if (!c) return fail(S2MV_ERR_BAD_PARAM, "null ctx");
+    if (!c->configured) return fail(S2MV_ERR_NOT_CONFIGURED, "not configured");
+    if (!c->taps) return fail(S2MV_ERR_BAD_PARAM, "taps not enabled (s2mv_enable_taps)");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    const s2mv_params &p = c->prm;
+    const size_t n = (size_t)p.num_rows * p.num_cols;
+    float *wta[2] = {wta_l, wta_r}, *irv[2] = {irv_l, irv_r}, *mask[2] = {mask_l, mask_r};
+    uint8_t *outl[2] = {outliers_l, outliers_r}, *arms[2] = {arms_l, arms_r};
+    for (int v = 0; v < 2; ++v) {
+        if (wta[v]) CU(cudaMemcpy(wta[v], c->tap_wta[v], n * sizeof(float), cudaMemcpyDeviceToHost));
+        if (irv[v]) CU(cudaMemcpy(irv[v], c->tap_irv[v], n * sizeof(float), cudaMemcpyDeviceToHost));
+        if (outl[v]) CU(cudaMemcpy(outl[v], c->tap_outl[v], n, cudaMemcpyDeviceToHost));
+        if (mask[v]) CU(cudaMemcpy(mask[v], c->mask[v], n * sizeof(float), cudaMemcpyDeviceToHost));
+        if (arms[v]) {
+            uint8_t *d = nullptr;
+            CU(cudaMalloc((void **)&d, 4 * n));
+            k_arms_unpack<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->arms[v], d, n);
+            cudaError_t e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(arms[v], d, 4 * n, cudaMemcpyDeviceToHost, c->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+            cudaFree(d);
+            if (e != cudaSuccess) return fail(S2MV_ERR_CUDA, "arms tap: %s", cudaGetErrorString(e));
+        }
+    }
+    if (views) CU(cudaMemcpy(views, c->views, (size_t)p.num_views * n * 3, cudaMemcpyDeviceToHost));
+    return S2MV_OK;
+}
+
+#include "s2mv_stages.inl"
