@@ -11,6 +11,16 @@
 #   2. d_filter_bilateral.cu:41-220 (dead texture-reference variants, API
 #      removed in CUDA 12) is dropped from a scratch copy under $TMPDIR
 #   3. empty stub headers for the two OpenCV includes of d_io.h:9-10
+#   4. d_dr_irv.cu is compiled with -maxrregcount=64: dr_irv_pre_kernel is launched with
+#      32x32 = 1024 threads (d_dr_irv.cu:247-261) but, built -O3 for sm_100 by nvcc 12.9, needs
+#      76 registers per thread, so the launch fails ("too many resources requested") and -- the
+#      reference never checks launch errors -- region voting silently does nothing.  (Its
+#      original target, sm_30, caps a thread at 63 registers, so there it always launched.)
+# A second library, libs2mv_ref_q15.so, differs in ONE line: a __syncthreads()
+# between the shared-memory fill and its use in dr_irv_pre_kernel
+# (d_dr_irv.cu:168/170).  The unmodified kernel races there, so its
+# voted disparities are not a function of its inputs; the barrier build is the
+# deterministic reading that the oracle and the product are held to bit for bit.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 REF="${REF:-/root/reference}"
@@ -26,6 +36,8 @@ mkdir -p "$OUT" "$TMP/stubs/opencv2/core" "$TMP/obj"
 : > "$TMP/stubs/opencv2/core/core.hpp"
 : > "$TMP/stubs/opencv2/opencv.hpp"
 sed '41,220d' "$REF/d_filter_bilateral.cu" > "$TMP/d_filter_bilateral.cu"
+sed -n '170p' "$REF/d_dr_irv.cu" | grep -q '// Compute' || { echo "build_ref: d_dr_irv.cu layout changed" >&2; exit 1; }
+sed '169i\    __syncthreads();' "$REF/d_dr_irv.cu" > "$TMP/d_dr_irv_q15.cu"
 
 FLAGS=(-O3 -gencode arch=compute_100,code=sm_100 -dc --expt-relaxed-constexpr -w
        -Xcompiler -fPIC -I "$TMP/stubs" -I "$REF")
@@ -35,14 +47,22 @@ UNITS=(d_io d_alu d_ci_census d_ci_ad d_mux_multiview d_tx_scale d_ci_adcensus d
        d_demux_common d_filter d_filter_gaussian d_op d_dr_dcc d_dr_irv)
 pids=()
 for u in "${UNITS[@]}"; do
-    "$NVCC" "${FLAGS[@]}" "$REF/$u.cu" -o "$TMP/obj/$u.o" &
+    extra=()
+    [ "$u" = d_dr_irv ] && extra=(-maxrregcount=64)
+    "$NVCC" "${FLAGS[@]}" "${extra[@]}" "$REF/$u.cu" -o "$TMP/obj/$u.o" &
     pids+=($!)
 done
 "$NVCC" "${FLAGS[@]}" "$TMP/d_filter_bilateral.cu" -o "$TMP/obj/d_filter_bilateral.o" &
 pids+=($!)
 "$NVCC" "${FLAGS[@]}" "$HERE/ref_harness.cu" -o "$TMP/obj/ref_harness.o" &
 pids+=($!)
+mkdir -p "$TMP/q15"
+"$NVCC" "${FLAGS[@]}" -maxrregcount=64 "$TMP/d_dr_irv_q15.cu" -o "$TMP/q15/d_dr_irv.o" &
+pids+=($!)
 for p in "${pids[@]}"; do wait "$p"; done
 "$NVCC" -gencode arch=compute_100,code=sm_100 -shared -Xcompiler -fPIC "$TMP"/obj/*.o \
     -o "$OUT/libs2mv_ref.so" -lcudart
-echo "build_ref: wrote $OUT/libs2mv_ref.so"
+mv "$TMP/q15/d_dr_irv.o" "$TMP/obj/d_dr_irv.o"
+"$NVCC" -gencode arch=compute_100,code=sm_100 -shared -Xcompiler -fPIC "$TMP"/obj/*.o \
+    -o "$OUT/libs2mv_ref_q15.so" -lcudart
+echo "build_ref: wrote $OUT/libs2mv_ref.so and $OUT/libs2mv_ref_q15.so"

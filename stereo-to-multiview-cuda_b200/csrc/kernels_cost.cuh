@@ -266,6 +266,7 @@ k_vpass(const VArgs a)
         slot = (slot + 1 == R) ? 0 : slot + 1;
     }
     cp_async_commit();
+    cp_async_wait<0>();  // the steady-state wait below only covers rows fetched inside the loop
     // `r`/`slot` now name the next row to fetch (y + usd - 1 + PF at iteration y = y0 ... unless clipped)
     r = y0 + usd - 1 + kVPrefetch;
     slot = r % R;

@@ -307,8 +307,6 @@ static int set_smem(K kernel, size_t bytes)
 
 static int set_kernel_attrs()
 {
-    static bool done = false;  // per process and device; cheap to repeat per context
-    (void)done;
     const size_t big = 227 * 1024;
     TRY(set_smem(k_hpass<1, true, true, false>, big));
     TRY(set_smem(k_hpass<1, false, true, false>, big));

@@ -158,7 +158,7 @@ extern "C" int s2mv_ca_cross(s2mv_ctx *ctx, const uint8_t *img, uint8_t **cross,
     if (!img || !cross || !cost || !acost) return fail(S2MV_ERR_BAD_PARAM, "null argument");
     if (elem_sz != 3) return fail(S2MV_ERR_BAD_PARAM, "elem_sz must be 3");
     s2mv_ctx *c;
-    TRY(acquire(ctx, H, W, D, ctx && ctx->configured ? ctx->prm.zero_disp : D / 2, usd, &c));
+    TRY(acquire(ctx, H, W, D, D / 2, usd, &c));  // zero_disp plays no part in aggregation
     cudaStream_t st = c->stream;
     const CostPlan &pl = c->plan;
     const size_t n = (size_t)H * W;

@@ -1,0 +1,162 @@
+"""GPU parity of the whole frame path (the `adcensus_stm` replacement,
+d_io.cu:7-238) against the CPU oracle, through the C ABI with HOST buffers,
+plus size-independent properties at BASELINE.json's full sizes.
+
+Bars: WTA disparities, outlier labels, voted disparities,
+masks, warped views and the interlaced frame bit-exact (the oracle is fed the
+GPU's two exponential tables, the only arithmetic a CPU cannot reproduce);
+post-bilateral disparities bit-exact as well (same operation order).
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import DEFAULTS
+
+pytestmark = pytest.mark.gpu
+
+ALGO = {k: DEFAULTS[k] for k in ("ad_coeff", "census_coeff", "ucd", "lcd", "usd", "lsd", "thresh_s", "thresh_h")}
+
+
+def run_both(pipe, oracle, sbs, W, D, zd, Ho=None, Wo=None):
+    H = sbs.shape[0]
+    Ho, Wo = Ho or H, Wo or W
+    pipe.configure(num_rows=H, num_cols=W, num_rows_out=Ho, num_cols_out=Wo, num_disp=D, zero_disp=zd,
+                   num_views=8, angle=18, **ALGO)
+    pipe.enable_taps(True)
+    dl, dr, out = pipe.adcensus_stm(sbs)
+    taps = pipe.read_taps()
+    pipe.enable_taps(False)
+    luts = pipe.exp_tables()
+    o = oracle.adcensus_stm(sbs, W, Ho, Wo, num_views=8, angle=18, D=D, zd=zd, luts=luts, want_taps=True, **ALGO)
+    return (dl, dr, out, taps), o
+
+
+def assert_frame_equal(got, want):
+    dl, dr, out, taps = got
+    odl, odr, oout, otaps = want
+    for k in ("arms_l", "arms_r", "wta_l", "wta_r", "outliers_l", "outliers_r", "irv_l", "irv_r", "mask_l", "mask_r"):
+        assert np.array_equal(taps[k], otaps[k]), k
+    assert np.array_equal(dl, odl) and np.array_equal(dr, odr)
+    assert np.array_equal(taps["views"], otaps["views"])
+    assert np.array_equal(out, oout)
+
+
+def test_config1_bud_full_frame_bit_exact(pipe, oracle, bud_sbs):
+    # BASELINE config 1 (in-domain stand-in): bud_2 + bud_3, 640x384, D=64, zd=32
+    got, want = run_both(pipe, oracle, bud_sbs, 640, 64, 32)
+    assert_frame_equal(got, want)
+    assert pipe.last_launch_count > 0
+
+
+def test_fish_identical_pair(pipe, oracle, fish_sbs):
+    # the bundled fish_1/fish_2 are byte-identical images: zero disparity is a minimum everywhere
+    got, want = run_both(pipe, oracle, fish_sbs, 640, 64, 32)
+    assert_frame_equal(got, want)
+
+
+@pytest.mark.parametrize("H,W,D,zd,Ho,Wo", [(70, 200, 20, 7, 70, 200), (45, 331, 48, 24, 64, 400),
+                                            (64, 161, 128, 64, 64, 161), (33, 96, 5, 2, 33, 96)])
+def test_ragged_shapes_bit_exact(pipe, oracle, bud_sbs, H, W, D, zd, Ho, Wo):
+    sbs = np.ascontiguousarray(np.concatenate([bud_sbs[50:50 + H, 100:100 + W], bud_sbs[50:50 + H, 740:740 + W]], 1))
+    got, want = run_both(pipe, oracle, sbs, W, D, zd, Ho, Wo)
+    assert_frame_equal(got, want)
+
+
+def test_sbs_wider_than_two_views(pipe, oracle, bud_sbs):
+    # num_cols_sbs > 2*num_cols: the extra columns are ignored
+    W = 300
+    sbs = np.ascontiguousarray(bud_sbs[:64, :640])
+    got, want = run_both(pipe, oracle, sbs, W, 32, 16)
+    assert_frame_equal(got, want)
+
+
+def test_d256_multi_chunk_wta(pipe, oracle):
+    # num_disp > 128 splits the disparity axis over CTAs; WTA is then a 64-bit atomicMin on (cost, d)
+    from s2mv_b200_pkg import synth
+    sbs = synth.make_sbs(48, 320, 4000)
+    got, want = run_both(pipe, oracle, sbs, 320, 256, 128)
+    assert_frame_equal(got, want)
+
+
+def test_device_entry_points_match_host_entry(pipe, bud_sbs):
+    import torch
+    H, W = 384, 640
+    pipe.configure(num_rows=H, num_cols=W, num_disp=64, zero_disp=32, **ALGO)
+    dl, dr, out = pipe.adcensus_stm(bud_sbs)
+    d_sbs = torch.from_numpy(bud_sbs).cuda()
+    d_dl = torch.empty((H, W), dtype=torch.float32, device="cuda")
+    d_dr = torch.empty_like(d_dl)
+    d_out = torch.empty((H, W, 3), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    pipe.process_device(d_sbs.data_ptr(), 2 * W, d_dl.data_ptr(), d_dr.data_ptr(), d_out.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_dl.cpu().numpy(), dl) and np.array_equal(d_dr.cpu().numpy(), dr)
+    assert np.array_equal(d_out.cpu().numpy(), out)
+    # cost-volume leg alone returns the WTA disparities
+    pipe.enable_taps(True)
+    pipe.adcensus_stm(bud_sbs)
+    taps = pipe.read_taps()
+    pipe.enable_taps(False)
+    pipe.costvol_device(d_sbs.data_ptr(), 2 * W, d_dl.data_ptr(), d_dr.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_dl.cpu().numpy(), taps["wta_l"]) and np.array_equal(d_dr.cpu().numpy(), taps["wta_r"])
+
+
+def digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def test_config2_1080p_d128_costvol_vs_oracle(pipe, oracle, fish_sbs, bud_sbs):
+    # BASELINE config 2 geometry: 1920x1080, D=128, zd=64 (bundled 640x384 pair upscaled with the reference's
+    # bilinear formula).  fish is a degenerate pair (identical images), so bud is checked too.
+    import torch
+    from s2mv_b200_pkg import synth
+    for src in (fish_sbs, bud_sbs):
+        L = synth.upscale_bilinear(src[:, :640], 1080, 1920)
+        R = synth.upscale_bilinear(src[:, 640:], 1080, 1920)
+        sbs = np.ascontiguousarray(np.concatenate([L, R], axis=1))
+        pipe.configure(num_rows=1080, num_cols=1920, num_disp=128, zero_disp=64, **ALGO)
+        d_sbs = torch.from_numpy(sbs).cuda()
+        d_dl = torch.empty((1080, 1920), dtype=torch.float32, device="cuda")
+        d_dr = torch.empty_like(d_dl)
+        pipe.costvol_device(d_sbs.data_ptr(), 3840, d_dl.data_ptr(), d_dr.data_ptr(), 0)
+        pipe.synchronize()
+        odl, odr = oracle.costvol(L, R, 128, 64, luts=pipe.exp_tables(), **{k: ALGO[k] for k in
+                                  ("ad_coeff", "census_coeff", "ucd", "lcd", "usd", "lsd")})
+        assert np.array_equal(d_dl.cpu().numpy(), odl)       # WTA disparities bit-exact at full size
+        assert np.array_equal(d_dr.cpu().numpy(), odr)
+
+
+def test_config3_1080p_full_frame_properties(pipe, oracle):
+    # synthetic 1080p frame (config 3 generator): determinism, value ranges, pass-through of the outer views,
+    # and exact agreement with the oracle on the disparities the DIBR stages consume
+    from s2mv_b200_pkg import synth
+    sbs = synth.make_sbs(1080, 1920, 1000)
+    pipe.configure(num_rows=1080, num_cols=1920, num_disp=128, zero_disp=64, **ALGO)
+    pipe.enable_taps(True)
+    a = pipe.adcensus_stm(sbs)
+    taps = pipe.read_taps()
+    b = pipe.adcensus_stm(sbs)
+    pipe.enable_taps(False)
+    assert digest(*a) == digest(*b)
+    assert np.array_equal(taps["views"][0], sbs[:, 1920:]) and np.array_equal(taps["views"][7], sbs[:, :1920])
+    for k in ("wta_l", "wta_r", "irv_l", "irv_r"):
+        assert taps[k].min() >= -64 and taps[k].max() <= 63 and np.array_equal(taps[k], np.rint(taps[k]))
+    assert set(np.unique(taps["outliers_l"])) <= {0, 1, 2}
+    assert set(np.unique(taps["mask_l"])) <= {0.0, 1.0}
+    assert a[0].min() >= -64 and a[0].max() <= 63.001
+    # refinement + DIBR replayed on the CPU from the GPU's own WTA disparities
+    D, zd = 128, 64
+    for side in ("l", "r"):
+        arms = taps["arms_" + side]
+        assert np.array_equal(arms, oracle.cross_arms(sbs[:, :1920] if side == "l" else sbs[:, 1920:], 20.0, 6.0, 17, 9))
+    ol, orr = oracle.dcc(taps["wta_l"], taps["wta_r"])
+    assert np.array_equal(ol, taps["outliers_l"]) and np.array_equal(orr, taps["outliers_r"])
+    il, _ = oracle.irv(taps["wta_l"], ol, taps["arms_l"], 20, 0.4, D, zd, 17, 5)
+    assert np.array_equal(il, taps["irv_l"])
+    assert np.array_equal(oracle.bilateral(il, 7, 5.0, 10.0, D), a[0])
