@@ -101,6 +101,9 @@ int s2mv_synchronize(s2mv_ctx *ctx);
  * not enabled with s2mv_enable_timing(ctx, 1). */
 int s2mv_enable_timing(s2mv_ctx *ctx, int on);
 int s2mv_last_timings(s2mv_ctx *ctx, float ms[4]);
+/* the four cost-volume kernels of that call: [0] cost init + horizontal pass 1,
+ * [1] vertical pass 2, [2] vertical pass 3, [3] horizontal pass 4 + WTA */
+int s2mv_last_costvol_kernel_timings(s2mv_ctx *ctx, float ms[4]);
 /* number of kernels the last frame call launched */
 int s2mv_last_launch_count(const s2mv_ctx *ctx);
 

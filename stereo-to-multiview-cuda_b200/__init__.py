@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "s2mv_status_string", "s2mv_last_error", "s2mv_default_params", "s2mv_create", "s2mv_destroy",
     "s2mv_configure", "s2mv_arena_bytes", "s2mv_device_sm_count", "s2mv_process_sbs",
     "s2mv_process_sbs_device", "s2mv_costvol_device", "s2mv_synchronize", "s2mv_enable_timing",
-    "s2mv_last_timings", "s2mv_last_launch_count", "s2mv_get_exp_tables", "s2mv_enable_taps",
+    "s2mv_last_timings", "s2mv_last_costvol_kernel_timings", "s2mv_last_launch_count", "s2mv_get_exp_tables", "s2mv_enable_taps",
     "s2mv_read_taps", "s2mv_ci_adcensus", "s2mv_gray", "s2mv_census", "s2mv_ci_ad", "s2mv_ci_census",
     "s2mv_ca_cross", "s2mv_dc_wta", "s2mv_dr_dcc", "s2mv_dr_irv", "s2mv_filter_bilateral_1",
     "s2mv_dibr_occl", "s2mv_filter_bleed_1", "s2mv_dibr_occl_to_mask", "s2mv_filter_gaussian_1",
@@ -175,6 +175,11 @@ class Pipeline:
         _check(self._L.s2mv_last_timings(self._ctx, ms))
         return dict(zip(("prepare", "costvol", "refine", "dibr"), [float(x) for x in ms]))
 
+    def last_costvol_kernel_timings(self):
+        ms = (C.c_float * 4)()
+        _check(self._L.s2mv_last_costvol_kernel_timings(self._ctx, ms))
+        return dict(zip(("ci_h1", "v2", "v3", "h4_wta"), [float(x) for x in ms]))
+
     def exp_tables(self, ad_coeff=None, census_coeff=None):
         ad_coeff = self.params.ad_coeff if ad_coeff is None else ad_coeff
         census_coeff = self.params.census_coeff if census_coeff is None else census_coeff
@@ -184,6 +189,12 @@ class Pipeline:
         return la, lc
 
     # ---- frame entry points ---------------------------------------------
+    def adcensus_stm_into(self, img_sbs, disp_l, disp_r, interlaced):
+        """adcensus_stm with caller-owned host arrays (d_io.h:32-40): outputs are written in place.
+        Pinned arrays (e.g. numpy views of torch pinned tensors) are DMA'd without staging."""
+        H, Ws, _ = img_sbs.shape
+        _check(self._L.s2mv_process_sbs(self._ctx, _p(img_sbs), Ws, _p(disp_l), _p(disp_r), _p(interlaced)))
+
     def adcensus_stm(self, img_sbs, want_disp=True, want_interlaced=True):
         """Host arrays in/out, synchronous: the adcensus_stm contract (d_io.cu:7-238)."""
         p = self.params
@@ -197,15 +208,23 @@ class Pipeline:
         _check(self._L.s2mv_process_sbs(self._ctx, _p(img_sbs), Ws, _p(dl), _p(dr), _p(out)))
         return dl, dr, out
 
-    def process_device(self, d_sbs_ptr, num_cols_sbs, d_disp_l=0, d_disp_r=0, d_interlaced=0, stream=0):
+    @staticmethod
+    def _stream(stream):
+        # None -> the context's own stream (NULL in the C ABI); an integer is a cudaStream_t handle, where 0
+        # (what torch reports for its default stream) means the legacy default stream = cudaStreamLegacy (0x1)
+        if stream is None:
+            return C.c_void_p(0)
+        return C.c_void_p(int(stream) or 1)
+
+    def process_device(self, d_sbs_ptr, num_cols_sbs, d_disp_l=0, d_disp_r=0, d_interlaced=0, stream=None):
         """Raw device pointers (ints, e.g. torch.Tensor.data_ptr()), asynchronous on `stream`."""
         _check(self._L.s2mv_process_sbs_device(self._ctx, C.c_void_p(d_sbs_ptr), int(num_cols_sbs),
                                                C.c_void_p(d_disp_l), C.c_void_p(d_disp_r),
-                                               C.c_void_p(d_interlaced), C.c_void_p(stream)))
+                                               C.c_void_p(d_interlaced), self._stream(stream)))
 
-    def costvol_device(self, d_sbs_ptr, num_cols_sbs, d_disp_l=0, d_disp_r=0, stream=0):
+    def costvol_device(self, d_sbs_ptr, num_cols_sbs, d_disp_l=0, d_disp_r=0, stream=None):
         _check(self._L.s2mv_costvol_device(self._ctx, C.c_void_p(d_sbs_ptr), int(num_cols_sbs),
-                                           C.c_void_p(d_disp_l), C.c_void_p(d_disp_r), C.c_void_p(stream)))
+                                           C.c_void_p(d_disp_l), C.c_void_p(d_disp_r), self._stream(stream)))
 
     def read_taps(self):
         p = self.params

@@ -224,6 +224,7 @@ struct s2mv_ctx {
     size_t h_sbs_bytes = 0;
     // timing
     cudaEvent_t ev[5] = {};
+    cudaEvent_t kev[5] = {};  // around the four cost-volume kernels
     int launches = 0;
     float y_interval = 0.f;
 };
@@ -278,6 +279,7 @@ extern "C" int s2mv_create(s2mv_ctx **out, int device)
         return fail(S2MV_ERR_CUDA, "cudaStreamCreate failed");
     }
     for (int i = 0; i < 5; ++i) cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 5; ++i) cudaEventCreate(&c->kev[i]);
     *out = c;
     return S2MV_OK;
 }
@@ -288,8 +290,10 @@ extern "C" void s2mv_destroy(s2mv_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_arena(c);
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < 5; ++i) {
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+        if (c->kev[i]) cudaEventDestroy(c->kev[i]);
+    }
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -434,6 +438,14 @@ extern "C" int s2mv_last_timings(s2mv_ctx *c, float ms[4])
     return S2MV_OK;
 }
 
+extern "C" int s2mv_last_costvol_kernel_timings(s2mv_ctx *c, float ms[4])
+{
+    if (!c || !ms) return fail(S2MV_ERR_BAD_PARAM, "null argument");
+    if (!c->timing) return fail(S2MV_ERR_BAD_PARAM, "timing not enabled");
+    for (int i = 0; i < 4; ++i) CU(cudaEventElapsedTime(&ms[i], c->kev[i], c->kev[i + 1]));
+    return S2MV_OK;
+}
+
 // ------------------------------------------------------- stage launchers
 struct Dims { int H, W; };
 
@@ -482,8 +494,10 @@ static int launch_costvol(s2mv_ctx *c, float *dispL, float *dispR, cudaStream_t 
     }
     a.S = pl.S_ci;
     dim3 g1((W + pl.S_ci - 1) / pl.S_ci, H, 2 * pl.nchunks);
+    if (c->timing) CU(cudaEventRecord(c->kev[0], st));
     k_hpass<1, true, true, false><<<g1, kHThreads, pl.smem_ci, st>>>(a);
     KCHECK();
+    if (c->timing) CU(cudaEventRecord(c->kev[1], st));
 
     VArgs va;
     memset(&va, 0, sizeof(va));
@@ -497,6 +511,7 @@ static int launch_costvol(s2mv_ctx *c, float *dispL, float *dispR, cudaStream_t 
         }
         k_vpass<<<gv, kVThreads, pl.smem_v, st>>>(va);
         KCHECK();
+        if (c->timing) CU(cudaEventRecord(c->kev[2 + pass], st));
     }
 
     fill_hargs(c, a, H, W, p.zero_disp);
@@ -512,6 +527,7 @@ static int launch_costvol(s2mv_ctx *c, float *dispL, float *dispR, cudaStream_t 
     dim3 g4((W + pl.S_ld - 1) / pl.S_ld, H, 2 * pl.nchunks);
     k_hpass<0, true, false, true><<<g4, kHThreads, pl.smem_ld, st>>>(a);
     KCHECK();
+    if (c->timing) CU(cudaEventRecord(c->kev[4], st));
     c->launches += 4;
     if (pl.nchunks > 1) {
         k_wta_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->wta_key[0], dispL, p.zero_disp, n);
@@ -746,23 +762,31 @@ extern "C" int s2mv_process_sbs(s2mv_ctx *c, const uint8_t *img_sbs, int num_col
     for (int v = 0; v < 2; ++v)
         if (!c->h_disp[v]) CU(cudaMallocHost((void **)&c->h_disp[v], n * sizeof(float)));
     cudaStream_t st = c->stream;
-    cudaPointerAttributes attr;
-    bool pinned_in = cudaPointerGetAttributes(&attr, img_sbs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-    cudaGetLastError();
-    if (pinned_in) {
+    // Pinned caller buffers are DMA'd directly; pageable ones (cv::Mat::data in video_io.cpp:139-146)
+    // are staged through the context's pinned buffers.
+    auto is_pinned = [](const void *ptr) {
+        if (!ptr) return false;
+        cudaPointerAttributes attr;
+        bool ok = cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        return ok;
+    };
+    const bool pin_in = is_pinned(img_sbs), pin_dl = is_pinned(disp_l), pin_dr = is_pinned(disp_r),
+               pin_out = is_pinned(interlaced);
+    if (pin_in) {
         CU(cudaMemcpyAsync(c->sbs, img_sbs, sbs_bytes, cudaMemcpyHostToDevice, st));
     } else {
         memcpy(c->h_sbs, img_sbs, sbs_bytes);
         CU(cudaMemcpyAsync(c->sbs, c->h_sbs, sbs_bytes, cudaMemcpyHostToDevice, st));
     }
     TRY(run_frame(c, c->sbs, num_cols_sbs, c->dispF[0], c->dispF[1], c->interlaced, false, st));
-    if (disp_l) CU(cudaMemcpyAsync(c->h_disp[0], c->dispF[0], n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (disp_r) CU(cudaMemcpyAsync(c->h_disp[1], c->dispF[1], n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (interlaced) CU(cudaMemcpyAsync(c->h_interlaced, c->interlaced, out_bytes, cudaMemcpyDeviceToHost, st));
+    if (disp_l) CU(cudaMemcpyAsync(pin_dl ? disp_l : c->h_disp[0], c->dispF[0], n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (disp_r) CU(cudaMemcpyAsync(pin_dr ? disp_r : c->h_disp[1], c->dispF[1], n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (interlaced) CU(cudaMemcpyAsync(pin_out ? interlaced : c->h_interlaced, c->interlaced, out_bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (disp_l) memcpy(disp_l, c->h_disp[0], n * sizeof(float));
-    if (disp_r) memcpy(disp_r, c->h_disp[1], n * sizeof(float));
-    if (interlaced) memcpy(interlaced, c->h_interlaced, out_bytes);
+    if (disp_l && !pin_dl) memcpy(disp_l, c->h_disp[0], n * sizeof(float));
+    if (disp_r && !pin_dr) memcpy(disp_r, c->h_disp[1], n * sizeof(float));
+    if (interlaced && !pin_out) memcpy(interlaced, c->h_interlaced, out_bytes);
     return S2MV_OK;
 }
 

@@ -124,7 +124,7 @@ def test_config2_1080p_d128_costvol_vs_oracle(pipe, oracle, fish_sbs, bud_sbs):
         d_sbs = torch.from_numpy(sbs).cuda()
         d_dl = torch.empty((1080, 1920), dtype=torch.float32, device="cuda")
         d_dr = torch.empty_like(d_dl)
-        pipe.costvol_device(d_sbs.data_ptr(), 3840, d_dl.data_ptr(), d_dr.data_ptr(), 0)
+        pipe.costvol_device(d_sbs.data_ptr(), 3840, d_dl.data_ptr(), d_dr.data_ptr(), None)
         pipe.synchronize()
         odl, odr = oracle.costvol(L, R, 128, 64, luts=pipe.exp_tables(), **{k: ALGO[k] for k in
                                   ("ad_coeff", "census_coeff", "ucd", "lcd", "usd", "lsd")})
