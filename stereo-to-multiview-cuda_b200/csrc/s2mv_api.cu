@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "kernels_cost.cuh"
 #include "kernels_dibr.cuh"
+#include "kernels_line.cuh"
 #include "kernels_prep.cuh"
 #include "kernels_refine.cuh"
 
@@ -113,9 +114,10 @@ static void host_gaussian_1d(std::vector<float> &k, int size, float sigma)
 
 // ------------------------------------------------------------ cost plan
 struct CostPlan {
-    int D, Dp, LP, LPtot, nchunks, usd, M, S_ci, S_ld;
-    size_t smem_ci, smem_ld, smem_v;
-    int nbands, rows_per_band;
+    int D, Dp, LP, LPtot, nchunks, usd, M, S_ci;
+    size_t smem_ci;                     // CI-only stage kernels (k_hpass)
+    int S_h, S_v;                       // outputs per CTA along a row / a column (k_line)
+    size_t smem_line_ci, smem_line_h, smem_line_v;
 };
 
 static size_t hpass_smem(int S, int halo, int Dc, int M, bool ci)
@@ -146,8 +148,29 @@ static int pick_segment(int W, int halo, int Dc, int M, bool ci, int LP, size_t 
     return 0;
 }
 
+// Segment length for k_line along a line of `len` outputs: the longest multiple of 4 whose tile lets
+// three CTAs share an SM (two, then one, when the halo is too wide for that), then evened out so the
+// last segment of the line is not a sliver.
+static int pick_line_segment(int len, int halo, int LP, bool ci, size_t *smem_out)
+{
+    const size_t budgets[3] = {73 * 1024, 110 * 1024, 224 * 1024};
+    for (int b = 0; b < 3; ++b) {
+        int smax = 0;
+        for (int S = 4; S <= 512; S += 4)
+            if (line_smem_bytes(S, halo, LP, ci) <= budgets[b]) smax = S;
+        if (smax == 0 || (smax < 2 * halo && b < 2 && smax < len)) continue;
+        const int nseg = (len + smax - 1) / smax;
+        int S = (((len + nseg - 1) / nseg) + 3) & ~3;
+        if (S > smax) S = smax;
+        *smem_out = line_smem_bytes(S, halo, LP, ci);
+        return S;
+    }
+    return 0;
+}
+
 static int make_plan(CostPlan &pl, int H, int W, int D, int zd, int usd, int sm_count)
 {
+    (void)sm_count;
     if (D < 1 || zd < 0 || zd > D || usd < 0 || usd > 64) return fail(S2MV_ERR_BAD_PARAM, "num_disp/zero_disp/usd out of range");
     pl.D = D;
     pl.usd = usd;
@@ -166,21 +189,11 @@ static int make_plan(CostPlan &pl, int H, int W, int D, int zd, int usd, int sm_
     pl.M = zd > D - 1 - zd ? zd : D - 1 - zd;
     if (pl.M < 0) pl.M = 0;
     pl.S_ci = pick_segment(W, usd, 4 * pl.LP, pl.M, true, pl.LP, &pl.smem_ci);
-    pl.S_ld = pick_segment(W, usd, 4 * pl.LP, pl.M, false, pl.LP, &pl.smem_ld);
-    if (!pl.S_ci || !pl.S_ld) return fail(S2MV_ERR_BAD_PARAM, "tile does not fit shared memory");
-    pl.smem_v = (size_t)(2 * usd + kVPrefetch) * kVThreads * sizeof(float4);
-    if (pl.smem_v > 220 * 1024) return fail(S2MV_ERR_BAD_PARAM, "usd too large for the vertical ring");
-    // enough CTAs for ~8 waves, bands not shorter than 4*usd rows
-    long ctas_per_band = (((long)W * pl.LPtot + kVThreads - 1) / kVThreads) * 2;
-    int resident = (int)(220 * 1024 / pl.smem_v);
-    if (resident > 16) resident = 16;
-    long want = (long)sm_count * resident * 8;
-    int nb = (int)((want + ctas_per_band - 1) / ctas_per_band);
-    int maxb = H / (4 * usd > 0 ? 4 * usd : 1);
-    if (nb > maxb) nb = maxb;
-    if (nb < 1) nb = 1;
-    pl.rows_per_band = (H + nb - 1) / nb;
-    pl.nbands = (H + pl.rows_per_band - 1) / pl.rows_per_band;
+    if (!pl.S_ci) return fail(S2MV_ERR_BAD_PARAM, "tile does not fit shared memory");
+    pl.S_h = pick_line_segment(W, usd, pl.LP, true, &pl.smem_line_ci);
+    pl.smem_line_h = line_smem_bytes(pl.S_h, usd, pl.LP, false);
+    pl.S_v = pick_line_segment(H, usd, pl.LP, false, &pl.smem_line_v);
+    if (!pl.S_h || !pl.S_v) return fail(S2MV_ERR_BAD_PARAM, "usd too large for the shared-memory tile");
     return S2MV_OK;
 }
 
@@ -309,19 +322,49 @@ static int set_smem(K kernel, size_t bytes)
     return S2MV_OK;
 }
 
+template <int LP>
+static int set_line_attrs()
+{
+    const size_t big = 227 * 1024;
+    TRY(set_smem(k_line<LM_CI_H, LP>, big));
+    TRY(set_smem(k_line<LM_H, LP>, big));
+    TRY(set_smem(k_line<LM_H_WTA, LP>, big));
+    TRY(set_smem(k_line<LM_V, LP>, big));
+    return S2MV_OK;
+}
+
 static int set_kernel_attrs()
 {
     const size_t big = 227 * 1024;
-    TRY(set_smem(k_hpass<1, true, true, false>, big));
     TRY(set_smem(k_hpass<1, false, true, false>, big));
     TRY(set_smem(k_hpass<2, false, true, false>, big));
     TRY(set_smem(k_hpass<3, false, true, false>, big));
-    TRY(set_smem(k_hpass<0, true, true, false>, big));
-    TRY(set_smem(k_hpass<0, true, false, true>, big));
-    TRY(set_smem(k_vpass, big));
+    TRY(set_line_attrs<1>());
+    TRY(set_line_attrs<2>());
+    TRY(set_line_attrs<4>());
+    TRY(set_line_attrs<8>());
+    TRY(set_line_attrs<16>());
+    TRY(set_line_attrs<32>());
     TRY(set_smem(k_bilateral, 160 * 1024));
     TRY(set_smem(k_gauss_dilate, 160 * 1024));
     TRY(set_smem(k_irv_vote, 64 * 1024));
+    return S2MV_OK;
+}
+
+// k_line<MODE, LP> for the plan's LP
+template <int MODE>
+static int launch_line(const CostPlan &pl, dim3 grid, size_t smem, cudaStream_t st, const LineArgs &a)
+{
+    switch (pl.LP) {
+        case 1: k_line<MODE, 1><<<grid, kLineThreads, smem, st>>>(a); break;
+        case 2: k_line<MODE, 2><<<grid, kLineThreads, smem, st>>>(a); break;
+        case 4: k_line<MODE, 4><<<grid, kLineThreads, smem, st>>>(a); break;
+        case 8: k_line<MODE, 8><<<grid, kLineThreads, smem, st>>>(a); break;
+        case 16: k_line<MODE, 16><<<grid, kLineThreads, smem, st>>>(a); break;
+        case 32: k_line<MODE, 32><<<grid, kLineThreads, smem, st>>>(a); break;
+        default: return fail(S2MV_ERR_BAD_PARAM, "unsupported lane count %d", pl.LP);
+    }
+    KCHECK();
     return S2MV_OK;
 }
 
@@ -478,7 +521,56 @@ static void fill_hargs(const s2mv_ctx *c, HArgs &a, int H, int W, int zd)
     a.halo = pl.usd; a.M = pl.M; a.view_first = 0;
 }
 
-// CI + H, V, V, H + WTA for both views: volA <- CI+H1; volB <- V(volA); volA <- V(volB); disp <- WTA(H(volA))
+static void fill_largs(const s2mv_ctx *c, LineArgs &a, int H, int W, int zd, float ad_coeff)
+{
+    const CostPlan &pl = c->plan;
+    memset(&a, 0, sizeof(a));
+    a.pixL = c->pix[0]; a.pixR = c->pix[1]; a.cenL = c->cen[0]; a.cenR = c->cen[1];
+    a.lutAd = c->lutAd; a.lutCen = c->lutCen;
+    a.inv_ad = (float)(1.0 / ad_coeff);  // d_ci_adcensus.cu:160 (see build_luts)
+    a.H = H; a.W = W; a.D = pl.D; a.zd = zd;
+    a.LPtot = pl.LPtot; a.nchunks = pl.nchunks;
+    a.halo = pl.usd; a.view_first = 0;
+}
+
+// The four aggregation passes over volume buffers A/B for `nviews` view slots (H, V, V, H;
+// d_ca_cross.cu:255-271).  from_ci: pass 1 builds its input in shared memory (A is only written).
+// to_wta: pass 4 reduces to disparities instead of storing (A is only read).
+static int launch_aggregate(s2mv_ctx *c, LineArgs a, float4 *A, float4 *B, size_t view_stride4, int nviews,
+                            bool from_ci, bool to_wta, cudaStream_t st)
+{
+    const CostPlan &pl = c->plan;
+    const int H = a.H, W = a.W;
+    const dim3 gh((W + pl.S_h - 1) / pl.S_h, H, nviews * pl.nchunks);
+    const dim3 gv(W, (H + pl.S_v - 1) / pl.S_v, nviews * pl.nchunks);
+    // pass 1: (CI ->) H : . -> A      [stage API: B -> A is not needed; input planes are loaded into B]
+    a.S = pl.S_h;
+    for (int v = 0; v < nviews; ++v) { a.in[v] = B + v * view_stride4; a.out[v] = A + v * view_stride4; }
+    if (c->timing) CU(cudaEventRecord(c->kev[0], st));
+    if (from_ci) TRY(launch_line<LM_CI_H>(pl, gh, pl.smem_line_ci, st, a));
+    else TRY(launch_line<LM_H>(pl, gh, pl.smem_line_h, st, a));
+    if (c->timing) CU(cudaEventRecord(c->kev[1], st));
+    // passes 2, 3: V : A -> B, B -> A
+    a.S = pl.S_v;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int v = 0; v < nviews; ++v) {
+            a.in[v] = (pass == 0 ? A : B) + v * view_stride4;
+            a.out[v] = (pass == 0 ? B : A) + v * view_stride4;
+        }
+        TRY(launch_line<LM_V>(pl, gv, pl.smem_line_v, st, a));
+        if (c->timing) CU(cudaEventRecord(c->kev[2 + pass], st));
+    }
+    // pass 4: H : A -> B, or A -> disparities
+    a.S = pl.S_h;
+    for (int v = 0; v < nviews; ++v) { a.in[v] = A + v * view_stride4; a.out[v] = B + v * view_stride4; }
+    if (to_wta) TRY(launch_line<LM_H_WTA>(pl, gh, pl.smem_line_h, st, a));
+    else TRY(launch_line<LM_H>(pl, gh, pl.smem_line_h, st, a));
+    if (c->timing) CU(cudaEventRecord(c->kev[4], st));
+    c->launches += 4;
+    return S2MV_OK;
+}
+
+// CI + H, V, V, H + WTA for both views: A <- CI+H; B <- V(A); A <- V(B); disp <- WTA(H(A))
 static int launch_costvol(s2mv_ctx *c, float *dispL, float *dispR, cudaStream_t st)
 {
     const s2mv_params &p = c->prm;
@@ -486,49 +578,16 @@ static int launch_costvol(s2mv_ctx *c, float *dispL, float *dispR, cudaStream_t 
     const int H = p.num_rows, W = p.num_cols;
     const size_t n = (size_t)H * W, view_stride4 = n * pl.LPtot;
     float4 *A = reinterpret_cast<float4 *>(c->vol[0]), *B = reinterpret_cast<float4 *>(c->vol[1]);
-    HArgs a;
-    fill_hargs(c, a, H, W, p.zero_disp);
+    LineArgs a;
+    fill_largs(c, a, H, W, p.zero_disp, p.ad_coeff);
     for (int v = 0; v < 2; ++v) {
-        a.out[v] = A + v * view_stride4;
-        a.arms[v] = c->arms[v];
-    }
-    a.S = pl.S_ci;
-    dim3 g1((W + pl.S_ci - 1) / pl.S_ci, H, 2 * pl.nchunks);
-    if (c->timing) CU(cudaEventRecord(c->kev[0], st));
-    k_hpass<1, true, true, false><<<g1, kHThreads, pl.smem_ci, st>>>(a);
-    KCHECK();
-    if (c->timing) CU(cudaEventRecord(c->kev[1], st));
-
-    VArgs va;
-    memset(&va, 0, sizeof(va));
-    va.H = H; va.W = W; va.LPtot = pl.LPtot; va.usd = pl.usd; va.rows_per_band = pl.rows_per_band;
-    dim3 gv((unsigned)(((size_t)W * pl.LPtot + kVThreads - 1) / kVThreads), pl.nbands, 2);
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int v = 0; v < 2; ++v) {
-            va.in[v] = (pass == 0 ? A : B) + v * view_stride4;
-            va.out[v] = (pass == 0 ? B : A) + v * view_stride4;
-            va.arms[v] = c->arms[v];
-        }
-        k_vpass<<<gv, kVThreads, pl.smem_v, st>>>(va);
-        KCHECK();
-        if (c->timing) CU(cudaEventRecord(c->kev[2 + pass], st));
-    }
-
-    fill_hargs(c, a, H, W, p.zero_disp);
-    for (int v = 0; v < 2; ++v) {
-        a.in[v] = A + v * view_stride4;
         a.arms[v] = c->arms[v];
         a.wta_key[v] = c->wta_key[v];
     }
     a.disp[0] = dispL; a.disp[1] = dispR;
-    a.S = pl.S_ld;
     if (pl.nchunks > 1)
         for (int v = 0; v < 2; ++v) CU(cudaMemsetAsync(c->wta_key[v], 0xff, n * sizeof(unsigned long long), st));
-    dim3 g4((W + pl.S_ld - 1) / pl.S_ld, H, 2 * pl.nchunks);
-    k_hpass<0, true, false, true><<<g4, kHThreads, pl.smem_ld, st>>>(a);
-    KCHECK();
-    if (c->timing) CU(cudaEventRecord(c->kev[4], st));
-    c->launches += 4;
+    TRY(launch_aggregate(c, a, A, B, view_stride4, 2, true, true, st));
     if (pl.nchunks > 1) {
         k_wta_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->wta_key[0], dispL, p.zero_disp, n);
         k_wta_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->wta_key[1], dispR, p.zero_disp, n);

@@ -177,30 +177,13 @@ extern "C" int s2mv_ca_cross(s2mv_ctx *ctx, const uint8_t *img, uint8_t **cross,
     dim3 gt((unsigned)((n + 31) / 32), (pl.Dp + 31) / 32);
     k_planes_to_vol<<<gt, dim3(32, 8), 0, st>>>(planes.as<float>(), c->vol[0], D, pl.Dp, n);
     KCHECK();
-    float4 *A = reinterpret_cast<float4 *>(c->vol[0]), *B = reinterpret_cast<float4 *>(c->vol[1]);
-    // H, V, V, H (d_ca_cross.cu:255-271)
-    HArgs a;
-    fill_hargs(c, a, H, W, c->prm.zero_disp);
+    // input planes were packed into vol[0]; the passes run vol[0] -> vol[1] -> ... and end in vol[1]
+    float4 *V0 = reinterpret_cast<float4 *>(c->vol[0]), *V1 = reinterpret_cast<float4 *>(c->vol[1]);
+    LineArgs a;
+    fill_largs(c, a, H, W, c->prm.zero_disp, c->prm.ad_coeff);
     a.arms[0] = c->arms[0];
-    a.S = pl.S_ld;
-    dim3 gh((W + pl.S_ld - 1) / pl.S_ld, H, pl.nchunks);
-    a.in[0] = A; a.out[0] = B;
-    k_hpass<0, true, true, false><<<gh, kHThreads, pl.smem_ld, st>>>(a);
-    KCHECK();
-    VArgs va;
-    memset(&va, 0, sizeof(va));
-    va.H = H; va.W = W; va.LPtot = pl.LPtot; va.usd = pl.usd; va.rows_per_band = pl.rows_per_band;
-    va.arms[0] = c->arms[0];
-    dim3 gv((unsigned)(((size_t)W * pl.LPtot + kVThreads - 1) / kVThreads), pl.nbands, 1);
-    va.in[0] = B; va.out[0] = A;
-    k_vpass<<<gv, kVThreads, pl.smem_v, st>>>(va);
-    KCHECK();
-    va.in[0] = A; va.out[0] = B;
-    k_vpass<<<gv, kVThreads, pl.smem_v, st>>>(va);
-    KCHECK();
-    a.in[0] = B; a.out[0] = A;
-    k_hpass<0, true, true, false><<<gh, kHThreads, pl.smem_ld, st>>>(a);
-    KCHECK();
+    // launch_aggregate reads pass 1 from its B and leaves pass 4 in its B: B = vol[0], A = vol[1]
+    TRY(launch_aggregate(c, a, V1, V0, 0, 1, false, false, st));
     k_vol_to_planes<<<gt, dim3(32, 8), 0, st>>>(c->vol[0], planes.as<float>(), D, pl.Dp, n);
     KCHECK();
     for (int d = 0; d < D; ++d) TRY(download(acost[d], planes.as<float>() + (size_t)d * n, n * sizeof(float), st));
