@@ -112,6 +112,10 @@ int s2mv_last_launch_count(const s2mv_ctx *ctx);
  * indexed by |dB|+|dG|+|dR| and 65 floats indexed by Hamming distance. */
 int s2mv_get_exp_tables(s2mv_ctx *ctx, float ad_coeff, float census_coeff,
                         float *lut_ad_766, float *lut_cen_65);
+/* The AD exponential term exactly as the fused cost-initialisation kernel
+ * evaluates it in place (no table; ex2.approx.ftz) for every |dB|+|dG|+|dR| in
+ * 0..765: must equal lut_ad_766 bit for bit (tests/test_gpu_stages.py). */
+int s2mv_get_ad_terms(s2mv_ctx *ctx, float ad_coeff, float *ad_terms_766);
 
 /* Taps on the last frame processed by this context (host destinations, any
  * may be NULL): WTA disparities, cross-check outliers, post-IRV disparities,

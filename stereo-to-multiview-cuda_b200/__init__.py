@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "s2mv_status_string", "s2mv_last_error", "s2mv_default_params", "s2mv_create", "s2mv_destroy",
     "s2mv_configure", "s2mv_arena_bytes", "s2mv_device_sm_count", "s2mv_process_sbs",
     "s2mv_process_sbs_device", "s2mv_costvol_device", "s2mv_synchronize", "s2mv_enable_timing",
-    "s2mv_last_timings", "s2mv_last_costvol_kernel_timings", "s2mv_last_launch_count", "s2mv_get_exp_tables", "s2mv_enable_taps",
+    "s2mv_last_timings", "s2mv_last_costvol_kernel_timings", "s2mv_last_launch_count", "s2mv_get_exp_tables", "s2mv_get_ad_terms", "s2mv_enable_taps",
     "s2mv_read_taps", "s2mv_ci_adcensus", "s2mv_gray", "s2mv_census", "s2mv_ci_ad", "s2mv_ci_census",
     "s2mv_ca_cross", "s2mv_dc_wta", "s2mv_dr_dcc", "s2mv_dr_irv", "s2mv_filter_bilateral_1",
     "s2mv_dibr_occl", "s2mv_filter_bleed_1", "s2mv_dibr_occl_to_mask", "s2mv_filter_gaussian_1",
@@ -187,6 +187,13 @@ class Pipeline:
         lc = np.zeros(65, np.float32)
         _check(self._L.s2mv_get_exp_tables(self._ctx, _f(ad_coeff), _f(census_coeff), _p(la), _p(lc)))
         return la, lc
+
+    def ad_terms(self, ad_coeff=None):
+        """The AD term as the fused kernel computes it in place, for sums 0..765."""
+        ad_coeff = self.params.ad_coeff if ad_coeff is None else ad_coeff
+        t = np.zeros(766, np.float32)
+        _check(self._L.s2mv_get_ad_terms(self._ctx, _f(ad_coeff), _p(t)))
+        return t
 
     # ---- frame entry points ---------------------------------------------
     def adcensus_stm_into(self, img_sbs, disp_l, disp_r, interlaced):

@@ -75,10 +75,17 @@ __device__ __forceinline__ float ad_term(int sad, float inv_ad)
 {
     // (float)sad without the conversion unit: exact for sad < 2^23
     const float f = __fsub_rn(__int_as_float(0x4B000000 | sad), 8388608.0f);
-    return ref_one_minus_exp(__fmul_rn(f, 0.33333333333f), inv_ad);
+    // ref_one_minus_exp with ex2.approx.ftz: the non-ftz form only differs (by its range-scaling
+    // prologue/epilogue, 3 extra instructions) when e = ex2(t) is subnormal, and then 1 - e rounds to
+    // 1.0f either way.  tests/test_gpu_stages.py compares all 766 values with the table.
+    float t = __fmul_rn(-__fmul_rn(f, 0.33333333333f), inv_ad);
+    t = __fmul_rn(t, 1.4426950408889634f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    return __fsub_rn(1.0f, e);
 }
 
-template <int LP, bool PLUS>
+template <int LP, bool PLUS, bool FULL_D>
 __device__ __forceinline__ void ci_fill_tile(float4 *__restrict__ C4, const uint32_t *__restrict__ sOwnP,
                                              const uint32_t *__restrict__ sOwnC, const uint32_t *__restrict__ sOthP,
                                              const uint32_t *__restrict__ sOthC, const float *__restrict__ sLutAd,
@@ -112,13 +119,16 @@ __device__ __forceinline__ void ci_fill_tile(float4 *__restrict__ C4, const uint
                 const int w = PLUS ? (i + j) : (4 + i - j);
                 const int sad = (int)__vsadu4(op[i], wp[w]);  // x byte is 0 in both
                 const uint32_t x = oc[i] ^ wc[w];
-                const int ham = __popc(x) + (int)((x >> 31) << 5);  // = ref_hamdist32 (d_alu.cu:7-15)
+                // ref_hamdist32 (d_alu.cu:7-15) = popc(x) + 32 * bit31(x), as a byte offset into the table
+                const uint32_t off = ((uint32_t)__popc(x) << 2) + ((x >> 31) << 7);
+                const float cen = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(sLutCen) + off);
 #ifdef S2MV_AD_LUT
                 const float ad = sLutAd[sad];
 #else
                 const float ad = ad_term(sad, inv_ad);
 #endif
-                r[j] = dv[j] ? __fadd_rn(ad, sLutCen[ham]) : 0.0f;
+                const float c = __fadd_rn(ad, cen);
+                r[j] = (FULL_D || dv[j]) ? c : 0.0f;
             }
             C4[(size_t)(p0 + i) * LP + q] = make_float4(r[0], r[1], r[2], r[3]);
         }
@@ -142,6 +152,7 @@ __device__ __forceinline__ void sum_group4(const float4 *__restrict__ base, cons
     const float4 *p = base + (size_t)lo * LP;
     int k = lo;
     if (cs < ce) {
+#pragma unroll 1
         for (; k < cs; ++k, p += LP) {  // head: every window still ends later, some have not started
             const float4 v = *p;
 #pragma unroll
@@ -154,6 +165,7 @@ __device__ __forceinline__ void sum_group4(const float4 *__restrict__ base, cons
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc4(acc[i], v);
         }
+#pragma unroll 1
         for (; k < hi; ++k, p += LP) {  // tail: every window has started, some have ended
             const float4 v = *p;
 #pragma unroll
@@ -161,6 +173,7 @@ __device__ __forceinline__ void sum_group4(const float4 *__restrict__ base, cons
                 if (k < e[i]) acc4(acc[i], v);
         }
     } else {
+#pragma unroll 1
         for (; k < hi; ++k, p += LP) {  // no common core (very short windows)
             const float4 v = *p;
 #pragma unroll
@@ -240,12 +253,12 @@ k_line(const LineArgs a)
         for (int i = tid; i < kAdLutSize; i += kLineThreads) sLutAd[i] = a.lutAd[i];
 #endif
         __syncthreads();
-        if (view == 0)
-            ci_fill_tile<LP, true>(C4, sOwnP, sOwnC, sOthP, sOthC, sLutAd, sLutCen, a.inv_ad, P4 / 4, team, q,
-                                   d0 + 4 * q, a.D);
-        else
-            ci_fill_tile<LP, false>(C4, sOwnP, sOwnC, sOthP, sOthC, sLutAd, sLutCen, a.inv_ad, P4 / 4, team, q,
-                                    d0 + 4 * q, a.D);
+        const bool full_d = d0 + Dc <= a.D;  // no padded disparities in this chunk
+#define S2MV_CI_FILL(PLUS, FULL) \
+    ci_fill_tile<LP, PLUS, FULL>(C4, sOwnP, sOwnC, sOthP, sOthC, sLutAd, sLutCen, a.inv_ad, P4 / 4, team, q, d0 + 4 * q, a.D)
+        if (view == 0) { if (full_d) S2MV_CI_FILL(true, true); else S2MV_CI_FILL(true, false); }
+        else           { if (full_d) S2MV_CI_FILL(false, true); else S2MV_CI_FILL(false, false); }
+#undef S2MV_CI_FILL
         __syncthreads();
         // the reference's 160-wide blocks read one slot outside their half at tx = 0 / 159.
         // Replay its flat indexing for those columns (they come in pairs 160m-1, 160m; at most three per

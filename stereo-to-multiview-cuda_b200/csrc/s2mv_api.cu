@@ -866,6 +866,28 @@ extern "C" int s2mv_get_exp_tables(s2mv_ctx *c, float ad_coeff, float census_coe
     return S2MV_OK;
 }
 
+__global__ void k_ad_terms(float inv_ad, float *__restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < kAdLutSize) out[i] = ad_term(i, inv_ad);
+}
+
+extern "C" int s2mv_get_ad_terms(s2mv_ctx *c, float ad_coeff, float *ad_terms)
+{
+    if (!c || !ad_terms) return fail(S2MV_ERR_BAD_PARAM, "null argument");
+    if (ad_coeff == 0.f) return fail(S2MV_ERR_BAD_PARAM, "ad_coeff must be non-zero");
+    CU(cudaSetDevice(c->device));
+    float *d = nullptr;
+    CU(cudaMalloc((void **)&d, 768 * sizeof(float)));
+    k_ad_terms<<<(kAdLutSize + 255) / 256, 256, 0, c->stream>>>((float)(1.0 / ad_coeff), d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ad_terms, d, kAdLutSize * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(S2MV_ERR_CUDA, "ad terms: %s", cudaGetErrorString(e));
+    return S2MV_OK;
+}
+
 extern "C" int s2mv_read_taps(s2mv_ctx *c, float *wta_l, float *wta_r, uint8_t *outliers_l, uint8_t *outliers_r,
                               float *irv_l, float *irv_r, uint8_t *arms_l, uint8_t *arms_r, float *mask_l,
                               float *mask_r, uint8_t *views)

@@ -68,6 +68,26 @@ def test_exp_tables_close_to_cpu(pipe, oracle):
         assert ga[0] == 0.0 and gc[0] == 0.0 and ga.min() >= 0.0 and ga.max() <= 1.0
 
 
+def test_in_kernel_ad_term_equals_table(pipe):
+    # the fused cost-initialisation kernel evaluates the AD exponential in place (ex2.approx.ftz, no
+    # table); it must reproduce the reference-sequence table bit for bit for every possible sum
+    for ad in (10.0, 5.0, 0.75, 30.0, 255.0, 1e-3):
+        table, _ = pipe.exp_tables(ad, 30.0)
+        assert np.array_equal(pipe.ad_terms(ad).view(np.uint32), table.view(np.uint32)), ad
+
+
+@pytest.mark.parametrize("usd,lsd", [(0, 0), (1, 1), (5, 3), (33, 17), (40, 9)])
+def test_ca_cross_halo_sizes(pipe, oracle, bud_sbs, usd, lsd):
+    # arm caps other than the default 17/9: tile halo, segment planning and window bounds all depend on usd
+    H, W, D, zd = 70, 333, 24, 12
+    L, R = pair(oracle, bud_sbs, H, W, 5)
+    cost, _ = oracle.ci_adcensus(L, R, D, zd, 10.0, 30.0)
+    arms, acost = pipe.ca_cross(L, cost, 20.0, 6.0, usd, lsd)
+    oarms = oracle.cross_arms(L, 20.0, 6.0, usd, lsd)
+    assert np.array_equal(arms, oarms)
+    assert np.array_equal(acost, oracle.ca_aggregate(cost, oarms))
+
+
 @pytest.mark.parametrize("H,W,D,zd", SHAPES)
 def test_ca_cross_bit_exact(pipe, oracle, bud_sbs, H, W, D, zd):
     L, R = pair(oracle, bud_sbs, H, W, 3)
