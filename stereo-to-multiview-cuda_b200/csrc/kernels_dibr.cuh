@@ -92,6 +92,68 @@ k_gauss_dilate(const float *__restrict__ in, float *__restrict__ out, const floa
     out[(size_t)gy * W + gx] = (va < q) ? q : va;
 }
 
+// Register-blocked form for a compile-time radius (see k_bilateral4): 4 adjacent outputs per thread,
+// tile values and kernel weights loaded by LDS.128 once per kernel row, one FFMA per tap.  `norm` — the
+// sequential fp32 sum of the weights, identical for every pixel — is computed once by the host in the
+// same order (host_kernel_norm) instead of 441 times per pixel.
+constexpr int kGa4W = 128, kGa4H = 8;
+
+template <int R>
+__global__ void __launch_bounds__(256)
+k_gauss_dilate4(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ kernel, float norm,
+                int invert, int H, int W)
+{
+    constexpr int KW = 2 * R + 1, KWP = (KW + 3) & ~3;
+    constexpr int TWP = (kGa4W + 2 * R + 3) & ~3, TH = kGa4H + 2 * R;
+    constexpr int NV = (4 + 2 * R + 3) & ~3;
+    static_assert(kGa4W - 4 + NV <= TWP, "row reads stay inside the padded tile");
+    extern __shared__ __align__(16) float gsm4[];
+    float *tile = gsm4, *sk = tile + TWP * TH;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int bx = blockIdx.x * kGa4W, by = blockIdx.y * kGa4H;
+    for (int i = tid; i < TWP * TH; i += 256) {
+        const int ty = i / TWP, tx = i - ty * TWP;
+        const float v = in[(size_t)clampi(by + ty - R, 0, H - 1) * W + clampi(bx + tx - R, 0, W - 1)];
+        tile[i] = invert ? __fsub_rn(1.0f, v) : v;
+    }
+    for (int i = tid; i < KWP * KW; i += 256) {
+        const int ky = i / KWP, kx = i - ky * KWP;
+        sk[i] = kx < KW ? kernel[ky * KW + kx] : 0.0f;
+    }
+    __syncthreads();
+    const int x0 = 4 * threadIdx.x, gx = bx + x0, gy = by + threadIdx.y;
+    if (gx >= W || gy >= H) return;
+    float res[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 1
+    for (int ky = 0; ky < KW; ++ky) {
+        float v[NV], w[KWP];
+        const float4 *trow = reinterpret_cast<const float4 *>(tile + (threadIdx.y + ky) * TWP + x0);
+        const float4 *wrow = reinterpret_cast<const float4 *>(sk + ky * KWP);
+#pragma unroll
+        for (int i = 0; i < NV / 4; ++i) {
+            const float4 t = trow[i];
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+#pragma unroll
+        for (int i = 0; i < KWP / 4; ++i) {
+            const float4 t = wrow[i];
+            w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int kx = 0; kx < KW; ++kx) res[o] = __fmaf_rn(v[o + kx], w[kx], res[o]);
+    }
+    float *o4 = out + (size_t)gy * W + gx;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        if (gx + o >= W) break;
+        const float va = tile[(threadIdx.y + R) * TWP + x0 + R + o];
+        const float q = __fdiv_rn(res[o], norm);
+        o4[o] = (va < q) ? q : va;
+    }
+}
+
 // One intermediate view per blockIdx.z: the two backward warps
 // (dibr_backward_warp_kernel, d_dibr_bwarp.cu:5-22) and the blend
 // (mux_merge_AB_kernel, d_mux_common.cu:23-46) of d_dibr_dbm, fused.

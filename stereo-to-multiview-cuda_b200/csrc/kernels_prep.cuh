@@ -79,6 +79,50 @@ k_census(const uint8_t *__restrict__ gray, OutT *__restrict__ census, int H, int
     census[(size_t)gy * W + gx] = c;
 }
 
+// Both views in one launch (blockIdx.z), low-32-bit form, gray staged in shared
+// memory: a 64x16 output tile reads a (64+8)x(16+4) byte tile once instead of
+// 32 clamped global byte loads per pixel.
+constexpr int kCenW = 64, kCenH = 16;
+__global__ void __launch_bounds__(kCenW *kCenH / 4)
+k_census_tile(const uint8_t *__restrict__ gray0, const uint8_t *__restrict__ gray1, uint32_t *__restrict__ cen0,
+              uint32_t *__restrict__ cen1, int H, int W)
+{
+    constexpr int TW = kCenW + 8, TH = kCenH + 4;  // rows y-1 .. y+3
+    __shared__ uint8_t tile[TH][TW];
+    const uint8_t *__restrict__ gray = blockIdx.z ? gray1 : gray0;
+    uint32_t *__restrict__ census = blockIdx.z ? cen1 : cen0;
+    const int bx = blockIdx.x * kCenW, by = blockIdx.y * kCenH;
+    const int tid = threadIdx.x, nt = kCenW * kCenH / 4;
+    for (int i = tid; i < TW * TH; i += nt) {
+        const int ty = i / TW, tx = i - ty * TW;
+        tile[ty][tx] = gray[(size_t)clampi(by + ty - 1, 0, H - 1) * W + clampi(bx + tx - 4, 0, W - 1)];
+    }
+    __syncthreads();
+    // tile[ty][tx] = gray[clamp(by + ty - 1)][clamp(bx + tx - 4)]: the reference's own coordinate clamp.
+    // Each thread: one column, 4 consecutive rows.
+    const int lx = tid % kCenW, ly0 = (tid / kCenW) * 4;
+    const int gx = bx + lx;
+    if (gx >= W) return;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ly = ly0 + j, gy = by + ly;
+        if (gy >= H) break;
+        const uint8_t centre = tile[ly + 1][lx + 4];
+        uint32_t c = 0;
+#pragma unroll
+        for (int y = -1; y <= 3; ++y) {
+            if (y == 0) continue;
+#pragma unroll
+            for (int x = -4; x <= 4; ++x) {
+                if (x == 0) continue;
+                c <<= 1;
+                if (tile[ly + 1 + y][lx + 4 + x] < centre) c += 1;
+            }
+        }
+        census[(size_t)gy * W + gx] = c;
+    }
+}
+
 // ca_cross_construction_kernel (d_ca_cross.cu:17-172): the arm is assigned
 // before the colour test, so it ends on the first failing pixel (Q6).
 __device__ __forceinline__ int max_abs_diff3(uint32_t a, uint32_t b)
@@ -120,6 +164,59 @@ k_arms(const uint32_t *__restrict__ pix, uint32_t *__restrict__ arms, float ucd,
     int d = arm_walk(pix, x, y, 0, +1, a, ucd, lcd, usd, lsd, H, W);
     int l = arm_walk(pix, x, y, -1, 0, a, ucd, lcd, usd, lsd, H, W);
     int r = arm_walk(pix, x, y, +1, 0, a, ucd, lcd, usd, lsd, H, W);
+    arms[(size_t)y * W + x] = (uint32_t)u | ((uint32_t)d << 8) | ((uint32_t)l << 16) | ((uint32_t)r << 24);
+}
+
+// Same arms, both views in one launch, pixels staged in shared memory: the walk
+// is a chain of up to 4*usd dependent loads; out of L2 each step costs ~600
+// cycles, out of shared memory ~30.
+constexpr int kArmW = 64, kArmH = 16;
+__device__ __forceinline__ int arm_walk_tile(const uint32_t *__restrict__ t, int pitch, int x, int y, int dx, int dy,
+                                             uint32_t anchor, float ucd, float lcd, int usd, int lsd, int H, int W)
+{
+    uint32_t prev = anchor;
+    int arm = 0;
+    const int step = dy * pitch + dx;
+    for (int s = 1; s <= usd; ++s) {
+        const int cx = x + dx * s, cy = y + dy * s;
+        if (cx < 0 || cx > W - 1 || cy < 0 || cy > H - 1) break;
+        arm = s;
+        const uint32_t c = t[s * step];
+        const float ac = (float)max_abs_diff3(c, anchor), cp = (float)max_abs_diff3(c, prev);
+        if (s > lsd) {
+            if (ac > ucd) break;
+        } else {
+            if (ac > lcd || cp > lcd) break;
+        }
+        prev = c;
+    }
+    return arm;
+}
+
+__global__ void __launch_bounds__(kArmW *kArmH)
+k_arms_tile(const uint32_t *__restrict__ pix0, const uint32_t *__restrict__ pix1, uint32_t *__restrict__ arms0,
+            uint32_t *__restrict__ arms1, float ucd, float lcd, int usd, int lsd, int H, int W)
+{
+    extern __shared__ uint32_t atile[];
+    const uint32_t *__restrict__ pix = blockIdx.z ? pix1 : pix0;
+    uint32_t *__restrict__ arms = blockIdx.z ? arms1 : arms0;
+    const int TW = kArmW + 2 * usd, TH = kArmH + 2 * usd;
+    const int bx = blockIdx.x * kArmW, by = blockIdx.y * kArmH;
+    const int tid = threadIdx.y * kArmW + threadIdx.x;
+    for (int i = tid; i < TW * TH; i += kArmW * kArmH) {
+        const int ty = i / TW, tx = i - ty * TW;
+        const int gx = bx + tx - usd, gy = by + ty - usd;
+        atile[i] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? pix[(size_t)gy * W + gx] : 0u;
+    }
+    __syncthreads();
+    const int x = bx + threadIdx.x, y = by + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const uint32_t *__restrict__ t = atile + (threadIdx.y + usd) * TW + threadIdx.x + usd;
+    const uint32_t a = *t;
+    const int u = arm_walk_tile(t, TW, x, y, 0, -1, a, ucd, lcd, usd, lsd, H, W);
+    const int d = arm_walk_tile(t, TW, x, y, 0, +1, a, ucd, lcd, usd, lsd, H, W);
+    const int l = arm_walk_tile(t, TW, x, y, -1, 0, a, ucd, lcd, usd, lsd, H, W);
+    const int r = arm_walk_tile(t, TW, x, y, +1, 0, a, ucd, lcd, usd, lsd, H, W);
     arms[(size_t)y * W + x] = (uint32_t)u | ((uint32_t)d << 8) | ((uint32_t)l << 16) | ((uint32_t)r << 24);
 }
 

@@ -38,33 +38,73 @@ k_dcc_merge(uint8_t *__restrict__ outL, uint8_t *__restrict__ outR, const uint8_
 
 // ---- iterative region voting (d_dr_irv.cu:17-43,134-269) -----------------
 // The reference gives every pixel a thread and every outlier thread a private
-// 65-int histogram in local memory.  Here the outliers (typically 10-20% of
-// the image, shrinking each iteration) are compacted into a list and each one
-// is voted on by a whole warp: lanes sweep the rows of the cross-shaped
-// support, the histogram lives in shared memory.  Votes read a snapshot and
-// are applied by a separate kernel (the race-free reading of Q15).
+// 65-int histogram in local memory, five times per view.  Here the outliers
+// are compacted ONCE into a list (they only ever shrink: a vote can clear an
+// outlier, nothing creates one); each iteration votes on the list — one warp
+// per outlier, one lane per row of its cross-shaped support so the dependent
+// arms -> disparity loads of different rows overlap, histogram in shared memory
+// — then applies the accepted votes and writes the survivors as the next
+// iteration's list.  Votes read a snapshot (separate kernels): the race-free
+// reading of Q15.
 struct IrvArgs {
     float *disp[2];
     uint8_t *outliers[2];
     const uint32_t *arms[2];
-    int *list[2];    // outlier pixel indices
-    int *vote[2];    // accepted disparity or kNoVote
-    int *count[2];   // list length
+    int *list[2];        // outlier pixel indices of this iteration
+    int *next[2];        // survivors (k_irv_apply)
+    int *vote[2];        // accepted disparity or kNoVote, per list entry
+    int *count[2];       // length of list
+    int *next_count[2];  // length of next
     int H, W, nbins, zd, usd, thresh_s;
     float thresh_h;
 };
 constexpr int kNoVote = -0x7fffffff;
 
+// append `mine` items per lane to a global list with one atomic per warp; returns this lane's base
+__device__ __forceinline__ int warp_append_base(int *counter, int mine)
+{
+    const int lane = threadIdx.x & 31;
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    int base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + incl - mine;
+}
+
+// 16 pixels per thread
 __global__ void __launch_bounds__(256)
 k_irv_compact(const IrvArgs a)
 {
     const int v = blockIdx.y;
     const size_t n = (size_t)a.H * a.W;
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (a.outliers[v][i] != 0) {
-        int k = atomicAdd(a.count[v], 1);
-        a.list[v][k] = (int)i;
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const uint8_t *__restrict__ outl = a.outliers[v];
+    uint32_t nz = 0;  // bit j: pixel i0 + j is an outlier
+    if (i0 + 16 <= n) {
+        const uint4 w = *reinterpret_cast<const uint4 *>(outl + i0);
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // high bit of every non-zero byte
+            const uint32_t hb = (((ws[k] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | ws[k]) & 0x80808080u;
+            nz |= (((hb >> 7) & 1u) | ((hb >> 14) & 2u) | ((hb >> 21) & 4u) | ((hb >> 28) & 8u)) << (4 * k);
+        }
+    } else {
+        for (int j = 0; j < 16; ++j)
+            if (i0 + j < n && outl[i0 + j] != 0) nz |= 1u << j;
+    }
+    int pos = warp_append_base(a.count[v], __popc(nz));
+    int *__restrict__ list = a.list[v];
+    while (nz) {
+        const int j = __ffs(nz) - 1;
+        nz &= nz - 1;
+        list[pos++] = (int)(i0 + j);
     }
 }
 
@@ -78,6 +118,7 @@ k_irv_vote(const IrvArgs a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int *hist = hist_all + warp * a.nbins;
     const int count = *a.count[v];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.next_count[v] = 0;  // consumed by k_irv_apply, which runs after
     const float *__restrict__ disp = a.disp[v];
     const uint8_t *__restrict__ outl = a.outliers[v];
     const uint32_t *__restrict__ arms = a.arms[v];
@@ -88,17 +129,19 @@ k_irv_vote(const IrvArgs a)
         for (int b = lane; b < a.nbins; b += 32) hist[b] = 0;
         __syncwarp();
         const uint32_t ac = arms[pix];
-        const int cu = min(arm_up(ac), a.usd), cd = arm_down(ac);
+        const int cu = min(arm_up(ac), a.usd), nrows = cu + arm_down(ac) + 1;  // rows [-cu, +cd] inclusive
         int cnt = 0;
-        for (int y = -cu; y <= cd; ++y) {
-            const size_t row = (size_t)(gy + y) * W;
+        for (int r = lane; r < nrows; r += 32) {
+            const size_t row = (size_t)(gy - cu + r) * W;
             const uint32_t ar = arms[row + gx];
             const int cl = arm_left(ar), span = cl + arm_right(ar) + 1;  // inclusive [-L, R]
-            for (int k = lane; k < span; k += 32) {
-                const size_t s = row + (gx - cl + k);
-                if (outl[s] == 0) {
-                    int bin = clampi((int)disp[s] + a.zd, 0, a.nbins - 1);
-                    atomicAdd(&hist[bin], 1);
+            const float *__restrict__ dp = disp + row + (gx - cl);
+            const uint8_t *__restrict__ op = outl + row + (gx - cl);
+#pragma unroll 4
+            for (int k = 0; k < span; ++k) {
+                const float dv = dp[k];
+                if (op[k] == 0) {
+                    atomicAdd(&hist[clampi((int)dv + a.zd, 0, a.nbins - 1)], 1);
                     ++cnt;
                 }
             }
@@ -133,13 +176,21 @@ k_irv_apply(const IrvArgs a)
 {
     const int v = blockIdx.y;
     const int count = *a.count[v];
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
-        const int vote = a.vote[v][e];
-        if (vote != kNoVote) {
-            const int pix = a.list[v][e];
-            a.outliers[v][pix] = 0;
-            a.disp[v][pix] = (float)vote;
+    const int stride = gridDim.x * blockDim.x;
+    for (int e0 = blockIdx.x * blockDim.x; e0 < count; e0 += stride) {  // block-uniform trip count
+        const int e = e0 + threadIdx.x;
+        int pix = -1;
+        if (e < count) {
+            const int vote = a.vote[v][e];
+            pix = a.list[v][e];
+            if (vote != kNoVote) {
+                a.outliers[v][pix] = 0;
+                a.disp[v][pix] = (float)vote;
+                pix = -1;
+            }
         }
+        const int pos = warp_append_base(a.next_count[v], pix >= 0 ? 1 : 0);
+        if (pix >= 0) a.next[v][pos] = pix;
     }
 }
 
@@ -180,6 +231,86 @@ k_bilateral(const float *__restrict__ in, float *__restrict__ out, const float *
         }
     }
     out[(size_t)gy * W + gx] = __fdiv_rn(res, norm);
+}
+
+// Register-blocked form for a compile-time radius: a thread produces 4 horizontally adjacent outputs.
+// Per kernel row it loads the 4 + 2R tile values they share and the row's 2R + 1 spatial weights with
+// LDS.128 (3.3 shared loads per 60 taps instead of 120); only the colour-table lookup stays per tap.
+// Each output still accumulates ky-major, kx-minor, exactly like the loop above.  Both views in one
+// launch (blockIdx.z).  BOUNDED: |a - s| < 2^23 and (int)|a - s| < ncolour are guaranteed by the caller
+// (disparities of this pipeline), so the index is taken with a round-toward-zero add instead of the
+// conversion unit and needs no clamp.
+constexpr int kBil4W = 128, kBil4H = 8;
+
+template <int R, bool BOUNDED>
+__global__ void __launch_bounds__(256)
+k_bilateral4(const float *__restrict__ in0, const float *__restrict__ in1, float *__restrict__ out0,
+             float *__restrict__ out1, const float *__restrict__ spatial, const float *__restrict__ colour,
+             int ncolour, int H, int W)
+{
+    constexpr int KW = 2 * R + 1, KWP = (KW + 3) & ~3;
+    constexpr int TWP = (kBil4W + 2 * R + 3) & ~3, TH = kBil4H + 2 * R;
+    constexpr int NV = (4 + 2 * R + 3) & ~3;  // tile values per thread per kernel row, rounded to float4s
+    static_assert(kBil4W - 4 + NV <= TWP, "row reads stay inside the padded tile");
+    extern __shared__ __align__(16) float bsm4[];
+    float *tile = bsm4, *ssp = tile + TWP * TH, *scol = ssp + KWP * KW;
+    const float *__restrict__ in = blockIdx.z ? in1 : in0;
+    float *__restrict__ out = blockIdx.z ? out1 : out0;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int bx = blockIdx.x * kBil4W, by = blockIdx.y * kBil4H;
+    for (int i = tid; i < TWP * TH; i += 256) {
+        const int ty = i / TWP, tx = i - ty * TWP;
+        tile[i] = in[(size_t)clampi(by + ty - R, 0, H - 1) * W + clampi(bx + tx - R, 0, W - 1)];
+    }
+    for (int i = tid; i < KWP * KW; i += 256) {
+        const int ky = i / KWP, kx = i - ky * KWP;
+        ssp[i] = kx < KW ? spatial[ky * KW + kx] : 0.0f;
+    }
+    for (int i = tid; i < ncolour; i += 256) scol[i] = colour[i];
+    __syncthreads();
+    const int x0 = 4 * threadIdx.x, gx = bx + x0, gy = by + threadIdx.y;
+    if (gx >= W || gy >= H) return;
+    float va[4], norm[4], res[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        va[o] = tile[(threadIdx.y + R) * TWP + x0 + R + o];
+        norm[o] = 0.0f;
+        res[o] = 0.0f;
+    }
+#pragma unroll 1
+    for (int ky = 0; ky < KW; ++ky) {
+        float v[NV], w[KWP];
+        const float4 *trow = reinterpret_cast<const float4 *>(tile + (threadIdx.y + ky) * TWP + x0);
+        const float4 *wrow = reinterpret_cast<const float4 *>(ssp + ky * KWP);
+#pragma unroll
+        for (int i = 0; i < NV / 4; ++i) {
+            const float4 t = trow[i];
+            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+#pragma unroll
+        for (int i = 0; i < KWP / 4; ++i) {
+            const float4 t = wrow[i];
+            w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+#pragma unroll
+            for (int kx = 0; kx < KW; ++kx) {
+                const float vs = v[o + kx];
+                const float ad = fabsf(__fsub_rn(va[o], vs));
+                int ci;
+                if (BOUNDED) ci = __float_as_int(__fadd_rz(ad, 8388608.0f)) & 0x7fffff;
+                else ci = min((int)ad, ncolour - 1);
+                const float wt = __fmul_rn(w[kx], scol[ci]);
+                norm[o] = __fadd_rn(norm[o], wt);
+                res[o] = __fmaf_rn(vs, wt, res[o]);
+            }
+        }
+    }
+    float *o4 = out + (size_t)gy * W + gx;
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+        if (gx + o < W) o4[o] = __fdiv_rn(res[o], norm[o]);
 }
 
 }  // namespace s2mv

@@ -223,8 +223,9 @@ struct s2mv_ctx {
     unsigned long long *wta_key[2] = {};
     float *disp[2] = {}, *dispF[2] = {};  // WTA/IRV disparities; bilateral output
     uint8_t *outl[2] = {}, *disoccl[2] = {};
-    int *irv_list[2] = {}, *irv_vote[2] = {}, *irv_count = nullptr;
+    int *irv_list[2] = {}, *irv_list2[2] = {}, *irv_vote[2] = {}, *irv_count = nullptr;
     float *bil_spatial = nullptr, *bil_colour = nullptr, *gauss_kernel = nullptr;
+    std::vector<float> h_gauss_kernel;  // host copy of gauss_kernel (for its fp32 sum)
     uint8_t *occl[2] = {}, *occlB[2] = {};
     float *mask[2] = {}, *tmask = nullptr;
     uint8_t *views = nullptr, *interlaced = nullptr;
@@ -346,8 +347,12 @@ static int set_kernel_attrs()
     TRY(set_line_attrs<16>());
     TRY(set_line_attrs<32>());
     TRY(set_smem(k_bilateral, 160 * 1024));
+    TRY(set_smem(k_bilateral4<7, true>, 64 * 1024));
+    TRY(set_smem(k_bilateral4<7, false>, 64 * 1024));
+    TRY(set_smem(k_gauss_dilate4<10>, 64 * 1024));
     TRY(set_smem(k_gauss_dilate, 160 * 1024));
     TRY(set_smem(k_irv_vote, 64 * 1024));
+    TRY(set_smem(k_arms_tile, 160 * 1024));
     return S2MV_OK;
 }
 
@@ -417,7 +422,8 @@ extern "C" int s2mv_configure(s2mv_ctx *c, const s2mv_params *p)
         TRY(dev_alloc_t(c, &c->dispF[v], n));
         TRY(dev_alloc_t(c, &c->outl[v], n));
         TRY(dev_alloc_t(c, &c->disoccl[v], n));
-        TRY(dev_alloc_t(c, &c->irv_list[v], n));
+        TRY(dev_alloc_t(c, &c->irv_list[v], n + 16));
+        TRY(dev_alloc_t(c, &c->irv_list2[v], n + 16));
         TRY(dev_alloc_t(c, &c->irv_vote[v], n));
         TRY(dev_alloc_t(c, &c->occl[v], n));
         TRY(dev_alloc_t(c, &c->occlB[v], n));
@@ -428,7 +434,7 @@ extern "C" int s2mv_configure(s2mv_ctx *c, const s2mv_params *p)
         if (pl.nchunks > 1) TRY(dev_alloc_t(c, &c->wta_key[v], n));
         TRY(dev_alloc_t(c, &c->vol[v], vol_elems));
     }
-    TRY(dev_alloc_t(c, &c->irv_count, 2));
+    TRY(dev_alloc_t(c, &c->irv_count, 4));
     TRY(dev_alloc_t(c, &c->tmask, n));
     TRY(dev_alloc_t(c, &c->lutAd, 768));
     TRY(dev_alloc_t(c, &c->lutCen, 68));
@@ -443,6 +449,7 @@ extern "C" int s2mv_configure(s2mv_ctx *c, const s2mv_params *p)
         TRY(dev_alloc_t(c, &c->bil_colour, k.size()));
         CU(cudaMemcpy(c->bil_colour, k.data(), k.size() * sizeof(float), cudaMemcpyHostToDevice));
         host_gaussian_kernel(k, p->mask_blur_radius, p->mask_blur_sigma);
+        c->h_gauss_kernel = k;
         TRY(dev_alloc_t(c, &c->gauss_kernel, k.size()));
         CU(cudaMemcpy(c->gauss_kernel, k.data(), k.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
@@ -492,6 +499,28 @@ extern "C" int s2mv_last_costvol_kernel_timings(s2mv_ctx *c, float ms[4])
 // ------------------------------------------------------- stage launchers
 struct Dims { int H, W; };
 
+static int launch_census(s2mv_ctx *c, const uint8_t *g0, const uint8_t *g1, uint32_t *c0, uint32_t *c1, int nviews,
+                         int H, int W, cudaStream_t st)
+{
+    k_census_tile<<<dim3((W + kCenW - 1) / kCenW, (H + kCenH - 1) / kCenH, nviews), kCenW * kCenH / 4, 0, st>>>(
+        g0, g1, c0, c1, H, W);
+    KCHECK();
+    c->launches += 1;
+    return S2MV_OK;
+}
+
+static int launch_arms(s2mv_ctx *c, const uint32_t *p0, const uint32_t *p1, uint32_t *a0, uint32_t *a1, int nviews,
+                       float ucd, float lcd, int usd, int lsd, int H, int W, cudaStream_t st)
+{
+    if (usd < 0 || usd > 64) return fail(S2MV_ERR_BAD_PARAM, "usd out of range");
+    const size_t smem = (size_t)(kArmW + 2 * usd) * (kArmH + 2 * usd) * sizeof(uint32_t);
+    k_arms_tile<<<dim3((W + kArmW - 1) / kArmW, (H + kArmH - 1) / kArmH, nviews), dim3(kArmW, kArmH), smem, st>>>(
+        p0, p1, a0, a1, ucd, lcd, usd, lsd, H, W);
+    KCHECK();
+    c->launches += 1;
+    return S2MV_OK;
+}
+
 static int launch_prepare(s2mv_ctx *c, const uint8_t *srcL, const uint8_t *srcR, size_t pitch, uint8_t *bgrL,
                           uint8_t *bgrR, cudaStream_t st)
 {
@@ -500,13 +529,9 @@ static int launch_prepare(s2mv_ctx *c, const uint8_t *srcL, const uint8_t *srcR,
     dim3 g((W + 255) / 256, H);
     k_unpack<<<g, 256, 0, st>>>(srcL, srcR, pitch, c->pix[0], c->pix[1], c->gray[0], c->gray[1], bgrL, bgrR, H, W);
     KCHECK();
-    for (int v = 0; v < 2; ++v) {
-        k_census<false, uint32_t><<<g, 256, 0, st>>>(c->gray[v], c->cen[v], H, W);
-        KCHECK();
-        k_arms<<<g, 256, 0, st>>>(c->pix[v], c->arms[v], p.ucd, p.lcd, p.usd, p.lsd, H, W);
-        KCHECK();
-    }
-    c->launches += 5;
+    c->launches += 1;
+    TRY(launch_census(c, c->gray[0], c->gray[1], c->cen[0], c->cen[1], 2, H, W, st));
+    TRY(launch_arms(c, c->pix[0], c->pix[1], c->arms[0], c->arms[1], 2, p.ucd, p.lcd, p.usd, p.lsd, H, W, st));
     return S2MV_OK;
 }
 
@@ -623,40 +648,87 @@ static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2],
     memset(&a, 0, sizeof(a));
     for (int v = 0; v < nviews; ++v) {
         a.disp[v] = disp[v]; a.outliers[v] = outl[v]; a.arms[v] = arms[v];
-        a.list[v] = c->irv_list[v]; a.vote[v] = c->irv_vote[v]; a.count[v] = c->irv_count + v;
+        a.list[v] = c->irv_list[v]; a.next[v] = c->irv_list2[v]; a.vote[v] = c->irv_vote[v];
+        a.count[v] = c->irv_count + v; a.next_count[v] = c->irv_count + 2 + v;
     }
     a.H = H; a.W = W; a.nbins = D > 65 ? D : 65; a.zd = zd; a.usd = usd; a.thresh_s = thresh_s; a.thresh_h = thresh_h;
     const size_t hist_bytes = (size_t)kIrvWarps * a.nbins * sizeof(int);
     if (hist_bytes > 64 * 1024) return fail(S2MV_ERR_BAD_PARAM, "num_disp too large for the voting histogram");
+    if (iterations <= 0) return S2MV_OK;
+    // outliers -> list, once; every iteration then votes on its list and leaves the survivors as the next one
+    CU(cudaMemsetAsync(c->irv_count, 0, 4 * sizeof(int), st));
+    k_irv_compact<<<dim3((unsigned)((n + 4095) / 4096), nviews), 256, 0, st>>>(a);
+    KCHECK();
+    c->launches += 1;
     for (int it = 0; it < iterations; ++it) {
-        CU(cudaMemsetAsync(c->irv_count, 0, 2 * sizeof(int), st));
-        k_irv_compact<<<dim3((unsigned)((n + 255) / 256), nviews), 256, 0, st>>>(a);
-        KCHECK();
         k_irv_vote<<<dim3(c->sm_count * 4, nviews), kIrvWarps * 32, hist_bytes, st>>>(a);
         KCHECK();
-        k_irv_apply<<<dim3(c->sm_count * 2, nviews), 256, 0, st>>>(a);
+        k_irv_apply<<<dim3(c->sm_count, nviews), 256, 0, st>>>(a);
         KCHECK();
-        c->launches += 3;
+        c->launches += 2;
+        for (int v = 0; v < nviews; ++v) {
+            int *t = a.list[v]; a.list[v] = a.next[v]; a.next[v] = t;
+            t = a.count[v]; a.count[v] = a.next_count[v]; a.next_count[v] = t;
+        }
     }
     return S2MV_OK;
 }
 
-static int launch_bilateral(s2mv_ctx *c, const float *in, float *out, const float *spatial, const float *colour,
-                            int radius, int ncolour, int H, int W, cudaStream_t st)
+// in/out per view slot (nviews = 1 or 2).  `bounded`: the inputs are this pipeline's own disparities
+// (|a - s| <= num_disp - 1), see k_bilateral4.
+static int launch_bilateral(s2mv_ctx *c, const float *const in[2], float *const out[2], int nviews,
+                            const float *spatial, const float *colour, int radius, int ncolour, bool bounded, int H,
+                            int W, cudaStream_t st)
 {
+    if (radius == 7 && (size_t)ncolour * sizeof(float) <= 32 * 1024) {
+        constexpr int R = 7, KW = 15, KWP = 16, TWP = (kBil4W + 2 * R + 3) & ~3, TH = kBil4H + 2 * R;
+        const size_t smem = ((size_t)TWP * TH + KWP * KW + ncolour) * sizeof(float);
+        dim3 g((W + kBil4W - 1) / kBil4W, (H + kBil4H - 1) / kBil4H, nviews);
+        if (bounded)
+            k_bilateral4<R, true><<<g, dim3(32, 8), smem, st>>>(in[0], in[nviews - 1], out[0], out[nviews - 1], spatial,
+                                                                 colour, ncolour, H, W);
+        else
+            k_bilateral4<R, false><<<g, dim3(32, 8), smem, st>>>(in[0], in[nviews - 1], out[0], out[nviews - 1], spatial,
+                                                                  colour, ncolour, H, W);
+        KCHECK();
+        c->launches += 1;
+        return S2MV_OK;
+    }
     const int tw = kBilW + 2 * radius, th = kBilH + 2 * radius, kw = 2 * radius + 1;
     size_t smem = ((size_t)tw * th + (size_t)kw * kw + ncolour) * sizeof(float);
     if (smem > 160 * 1024) return fail(S2MV_ERR_BAD_PARAM, "bilateral tile too large");
     dim3 g((W + kBilW - 1) / kBilW, (H + kBilH - 1) / kBilH);
-    k_bilateral<<<g, dim3(kBilW, kBilH), smem, st>>>(in, out, spatial, colour, radius, ncolour, H, W);
-    KCHECK();
-    c->launches += 1;
+    for (int v = 0; v < nviews; ++v) {
+        k_bilateral<<<g, dim3(kBilW, kBilH), smem, st>>>(in[v], out[v], spatial, colour, radius, ncolour, H, W);
+        KCHECK();
+        c->launches += 1;
+    }
     return S2MV_OK;
 }
 
-static int launch_gauss(s2mv_ctx *c, const float *in, float *out, const float *kernel, int radius, int invert, int H,
-                        int W, cudaStream_t st)
+// sum of the kernel weights exactly as every thread of filter_gaussian_1_kernel_1 accumulates it
+// (d_filter_gaussian.cu:60-80: row-major, fp32, from 0)
+static float host_kernel_norm(const float *k, int radius)
 {
+    const int kw = 2 * radius + 1;
+    volatile float norm = 0.0f;  // volatile: one rounded fp32 add per weight, never widened or reassociated
+    for (int i = 0; i < kw * kw; ++i) norm = norm + k[i];
+    return norm;
+}
+
+static int launch_gauss(s2mv_ctx *c, const float *in, float *out, const float *kernel, const float *host_kernel,
+                        int radius, int invert, int H, int W, cudaStream_t st)
+{
+    if (radius == 10 && host_kernel) {
+        constexpr int R = 10, KW = 21, KWP = 24, TWP = (kGa4W + 2 * R + 3) & ~3, TH = kGa4H + 2 * R;
+        const size_t smem = ((size_t)TWP * TH + KWP * KW) * sizeof(float);
+        dim3 g((W + kGa4W - 1) / kGa4W, (H + kGa4H - 1) / kGa4H);
+        k_gauss_dilate4<R><<<g, dim3(32, 8), smem, st>>>(in, out, kernel, host_kernel_norm(host_kernel, radius), invert,
+                                                          H, W);
+        KCHECK();
+        c->launches += 1;
+        return S2MV_OK;
+    }
     const int tw = kGaW + 2 * radius, th = kGaH + 2 * radius, kw = 2 * radius + 1;
     size_t smem = ((size_t)tw * th + (size_t)kw * kw) * sizeof(float);
     dim3 g((W + kGaW - 1) / kGaW, (H + kGaH - 1) / kGaH);
@@ -734,8 +806,12 @@ static int run_frame(s2mv_ctx *c, const uint8_t *d_sbs, int num_cols_sbs, float 
         for (int v = 0; v < 2; ++v)
             CU(cudaMemcpyAsync(c->tap_irv[v], c->disp[v], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
     float *fl = d_disp_l ? d_disp_l : c->dispF[0], *fr = d_disp_r ? d_disp_r : c->dispF[1];
-    TRY(launch_bilateral(c, c->disp[0], fl, c->bil_spatial, c->bil_colour, p.bilateral_radius, p.num_disp, H, W, st));
-    TRY(launch_bilateral(c, c->disp[1], fr, c->bil_spatial, c->bil_colour, p.bilateral_radius, p.num_disp, H, W, st));
+    {
+        const float *bin[2] = {c->disp[0], c->disp[1]};
+        float *bout[2] = {fl, fr};
+        TRY(launch_bilateral(c, bin, bout, 2, c->bil_spatial, c->bil_colour, p.bilateral_radius, p.num_disp, true, H, W,
+                             st));
+    }
     if (c->timing) CU(cudaEventRecord(c->ev[3], st));
 
     // DIBR (d_io.cu:160-191)
@@ -749,7 +825,8 @@ static int run_frame(s2mv_ctx *c, const uint8_t *d_sbs, int num_cols_sbs, float 
         KCHECK();
     }
     c->launches += 3;
-    TRY(launch_gauss(c, c->mask[1], c->tmask, c->gauss_kernel, p.mask_blur_radius, 1, H, W, st));
+    TRY(launch_gauss(c, c->mask[1], c->tmask, c->gauss_kernel, c->h_gauss_kernel.data(), p.mask_blur_radius, 1, H, W,
+                     st));
     if (V > 2) {
         DbmArgs d;
         memset(&d, 0, sizeof(d));

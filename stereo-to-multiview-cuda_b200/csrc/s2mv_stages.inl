@@ -69,10 +69,7 @@ int stage_ci(s2mv_ctx *user, const uint8_t *img_l, const uint8_t *img_r, float *
     k_unpack<<<g, 256, 0, st>>>(imgs.as<uint8_t>(), imgs.as<uint8_t>() + n * 3, (size_t)W * 3, c->pix[0], c->pix[1],
                                 c->gray[0], c->gray[1], nullptr, nullptr, H, W);
     KCHECK();
-    for (int v = 0; v < 2; ++v) {
-        k_census<false, uint32_t><<<g, 256, 0, st>>>(c->gray[v], c->cen[v], H, W);
-        KCHECK();
-    }
+    TRY(launch_census(c, c->gray[0], c->gray[1], c->cen[0], c->cen[1], 2, H, W, st));
     TRY(build_luts(c, ad_coeff, census_coeff, st));
     HArgs a;
     fill_hargs(c, a, H, W, zd);
@@ -172,8 +169,7 @@ extern "C" int s2mv_ca_cross(s2mv_ctx *ctx, const uint8_t *img, uint8_t **cross,
     k_unpack<<<g, 256, 0, st>>>(dimg.as<uint8_t>(), dimg.as<uint8_t>(), (size_t)W * 3, c->pix[0], c->pix[1],
                                 c->gray[0], c->gray[1], nullptr, nullptr, H, W);
     KCHECK();
-    k_arms<<<g, 256, 0, st>>>(c->pix[0], c->arms[0], ucd, lcd, usd, lsd, H, W);
-    KCHECK();
+    TRY(launch_arms(c, c->pix[0], c->pix[0], c->arms[0], c->arms[0], 1, ucd, lcd, usd, lsd, H, W, st));
     dim3 gt((unsigned)((n + 31) / 32), (pl.Dp + 31) / 32);
     k_planes_to_vol<<<gt, dim3(32, 8), 0, st>>>(planes.as<float>(), c->vol[0], D, pl.Dp, n);
     KCHECK();
@@ -276,7 +272,12 @@ extern "C" int s2mv_filter_bilateral_1(s2mv_ctx *ctx, float *img, int radius, fl
     TRY(upload(dsp.p, sp.data(), sp.size() * sizeof(float), st));
     TRY(upload(dcol.p, col.data(), col.size() * sizeof(float), st));
     TRY(upload(c->disp[0], img, n * sizeof(float), st));
-    TRY(launch_bilateral(c, c->disp[0], c->dispF[0], dsp.as<float>(), dcol.as<float>(), radius, num_disp, H, W, st));
+    {
+        // arbitrary caller data: index clamped, converted with cvt.rzi like the reference (not the bounded fast path)
+        const float *bin[2] = {c->disp[0], c->disp[0]};
+        float *bout[2] = {c->dispF[0], c->dispF[0]};
+        TRY(launch_bilateral(c, bin, bout, 1, dsp.as<float>(), dcol.as<float>(), radius, num_disp, false, H, W, st));
+    }
     TRY(download(img, c->dispF[0], n * sizeof(float), st));
     CU(cudaStreamSynchronize(st));
     return S2MV_OK;
@@ -356,7 +357,7 @@ extern "C" int s2mv_filter_gaussian_1(s2mv_ctx *ctx, float *img, int radius, flo
     TRY(dk.alloc(k.size() * sizeof(float)));
     TRY(upload(dk.p, k.data(), k.size() * sizeof(float), st));
     TRY(upload(c->mask[0], img, n * sizeof(float), st));
-    TRY(launch_gauss(c, c->mask[0], c->tmask, dk.as<float>(), radius, 0, H, W, st));
+    TRY(launch_gauss(c, c->mask[0], c->tmask, dk.as<float>(), k.data(), radius, 0, H, W, st));
     TRY(download(img, c->tmask, n * sizeof(float), st));
     CU(cudaStreamSynchronize(st));
     return S2MV_OK;
@@ -390,7 +391,7 @@ extern "C" int s2mv_dibr_dbm(s2mv_ctx *ctx, uint8_t *img_out, const uint8_t *img
     k_unpack<<<dim3((W + 255) / 256, H), 256, 0, st>>>(imgs.as<uint8_t>(), imgs.as<uint8_t>() + n * 3, (size_t)W * 3,
                                                       c->pix[0], c->pix[1], c->gray[0], c->gray[1], nullptr, nullptr, H, W);
     KCHECK();
-    TRY(launch_gauss(c, c->mask[1], c->tmask, dk.as<float>(), blur_radius, 1, H, W, st));
+    TRY(launch_gauss(c, c->mask[1], c->tmask, dk.as<float>(), k.data(), blur_radius, 1, H, W, st));
     DbmArgs d;
     memset(&d, 0, sizeof(d));
     d.pixL = c->pix[0]; d.pixR = c->pix[1]; d.dispL = c->dispF[0]; d.dispR = c->dispF[1];
