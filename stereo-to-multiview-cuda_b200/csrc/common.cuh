@@ -64,13 +64,28 @@ __device__ __forceinline__ void st_stream4(float4 *p, float4 v)
                  "f"(v.w) : "memory");
 }
 
-// Exact-order accumulate: plain IEEE adds, never contracted.
+// Exact-order accumulate: plain IEEE adds, never contracted.  sm_100a's packed add (FADD2: two
+// independent round-to-nearest fp32 adds per lane, one issue slot) halves the issue cost of the
+// aggregation loops, whose ceiling is instruction issue, not the FP32 pipe (tools/ubench_fadd2.cu).
+__device__ __forceinline__ void add2_rn(float &a0, float &a1, float v0, float v1)
+{
+    unsigned long long A, V;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(A) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(V) : "f"(v0), "f"(v1));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(A) : "l"(V));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(a0), "=f"(a1) : "l"(A));
+}
 __device__ __forceinline__ void acc4(float4 &a, const float4 v)
 {
+#ifdef S2MV_NO_FADD2
     a.x = __fadd_rn(a.x, v.x);
     a.y = __fadd_rn(a.y, v.y);
     a.z = __fadd_rn(a.z, v.z);
     a.w = __fadd_rn(a.w, v.w);
+#else
+    add2_rn(a.x, a.y, v.x, v.y);
+    add2_rn(a.z, a.w, v.z, v.w);
+#endif
 }
 
 }  // namespace s2mv
