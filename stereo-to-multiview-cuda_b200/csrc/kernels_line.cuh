@@ -62,7 +62,7 @@ struct LineArgs {
 __host__ __device__ inline size_t line_smem_bytes(int S, int halo, int LP, bool ci)
 {
     const size_t P4 = ((size_t)S + 2 * halo + 3) & ~(size_t)3;
-    size_t b = P4 * LP * 16 + (size_t)S * 4;
+    size_t b = P4 * LP * 16 + (size_t)S * 8;
     if (ci) b += (2 * P4 + 2 * (P4 + 4 * LP)) * 4 + (68 + 768) * 4;
     return b;
 }
@@ -137,49 +137,100 @@ __device__ __forceinline__ void ci_fill_tile(float4 *__restrict__ C4, const uint
 
 // The four window sums of one output group.  se[i] = start | end << 16 in tile
 // positions.  `base` already points at this lane's float4 of position 0.
-template <int LP>
-__device__ __forceinline__ void sum_group4(const float4 *__restrict__ base, const uint32_t se[4], float4 acc[4])
+//
+// Every accumulator's additions are one contiguous ascending run, so a group splits into
+//   private head [s_i, cs)  |  shared core [cs, ce)  |  private tail [ce, e_i)      cs = max s, ce = min e
+// and none of the three needs a per-position predicate.  In the common case the four starts and
+// the four ends are non-decreasing (neighbouring windows slide; 84-85 % of the groups of the bench
+// frame): the heads then form a staircase -- [s0,s1) feeds output 0, [s1,s2) outputs 0-1, [s2,s3)
+// outputs 0-2 -- and the tails its mirror image, so each tile position is still read exactly once
+// (one LDS.128 per position of the union) and every issued add is a useful one.  Other groups run
+// their heads and tails output by output; groups without a common core run four plain loops.
+// (The first formulation predicated 16 adds per position on four compares and spent 3/4 of its issue
+// slots on compares, loop control and masked-off adds: profiles/r1b_line_kernels_ncu_full.txt.)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int OFF>
+__device__ __forceinline__ float4 lds128(uint32_t addr)
 {
-    int s[4], e[4];
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(OFF));
+    return v;
+}
+
+// acc[i] += tile[p] for every output i in MASK, p = from, from + PB, ... < to (shared-memory byte addresses)
+template <int PB, int MASK>
+__device__ __forceinline__ void run_add(uint32_t &p, const uint32_t pend, float4 acc[4])
+{
+#pragma unroll 1
+    for (; p != pend; p += PB) {
+        const float4 v = lds128<0>(p);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        s[i] = (int)(se[i] & 0xffffu);
-        e[i] = (int)(se[i] >> 16);
-        acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i)
+            if (MASK & (1 << i)) acc4(acc[i], v);
     }
-    const int lo = min(min(s[0], s[1]), min(s[2], s[3])), cs = max(max(s[0], s[1]), max(s[2], s[3]));
-    const int ce = min(min(e[0], e[1]), min(e[2], e[3])), hi = max(max(e[0], e[1]), max(e[2], e[3]));
-    const float4 *p = base + (size_t)lo * LP;
-    int k = lo;
+}
+
+// s, e: window start / end of the four outputs as BYTE offsets into the tile (position * PB);
+// tq: shared-memory address of this lane's float4 of position 0.
+template <int LP>
+__device__ __forceinline__ void sum_group4(const uint32_t tq, const uint4 ws, const uint4 we, float4 acc[4])
+{
+    constexpr int PB = LP * 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t cs = max(max(ws.x, ws.y), max(ws.z, ws.w));
+    const uint32_t ce = min(min(we.x, we.y), min(we.z, we.w));
+    uint32_t p;
     if (cs < ce) {
-#pragma unroll 1
-        for (; k < cs; ++k, p += LP) {  // head: every window still ends later, some have not started
-            const float4 v = *p;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (k >= s[i]) acc4(acc[i], v);
+        const uint32_t pcs = tq + cs, pce = tq + ce;
+        const bool mono = ws.x <= ws.y && ws.y <= ws.z && ws.z <= ws.w && we.x <= we.y && we.y <= we.z && we.z <= we.w;
+        if (mono) {
+            p = tq + ws.x;
+            run_add<PB, 0x1>(p, tq + ws.y, acc);
+            run_add<PB, 0x3>(p, tq + ws.z, acc);
+            run_add<PB, 0x7>(p, pcs, acc);
+        } else {
+            p = tq + ws.x; run_add<PB, 0x1>(p, pcs, acc);
+            p = tq + ws.y; run_add<PB, 0x2>(p, pcs, acc);
+            p = tq + ws.z; run_add<PB, 0x4>(p, pcs, acc);
+            p = tq + ws.w; run_add<PB, 0x8>(p, pcs, acc);
+            p = pcs;
         }
-#pragma unroll 2
-        for (; k < ce; ++k, p += LP) {  // core: all four windows open
-            const float4 v = *p;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc4(acc[i], v);
-        }
+        // core: all four windows open; four positions in flight per trip
+        {
+            const uint32_t n4 = ((ce - cs) / (4 * PB)) * (4 * PB);
+            const uint32_t p4 = pcs + n4;
 #pragma unroll 1
-        for (; k < hi; ++k, p += LP) {  // tail: every window has started, some have ended
-            const float4 v = *p;
+            for (; p != p4; p += 4 * PB) {
+                const float4 v0 = lds128<0>(p), v1 = lds128<PB>(p), v2 = lds128<2 * PB>(p), v3 = lds128<3 * PB>(p);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (k < e[i]) acc4(acc[i], v);
+                for (int i = 0; i < 4; ++i) acc4(acc[i], v0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc4(acc[i], v1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc4(acc[i], v2);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc4(acc[i], v3);
+            }
+            run_add<PB, 0xf>(p, pce, acc);
+        }
+        if (mono) {
+            run_add<PB, 0xe>(p, tq + we.y, acc);
+            run_add<PB, 0xc>(p, tq + we.z, acc);
+            run_add<PB, 0x8>(p, tq + we.w, acc);
+        } else {
+            p = pce; run_add<PB, 0x1>(p, tq + we.x, acc);
+            p = pce; run_add<PB, 0x2>(p, tq + we.y, acc);
+            p = pce; run_add<PB, 0x4>(p, tq + we.z, acc);
+            p = pce; run_add<PB, 0x8>(p, tq + we.w, acc);
         }
     } else {
-#pragma unroll 1
-        for (; k < hi; ++k, p += LP) {  // no common core (very short windows)
-            const float4 v = *p;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (k >= s[i] && k < e[i]) acc4(acc[i], v);
-        }
+        // no common core (short, scattered windows): four plain runs
+        p = tq + ws.x; run_add<PB, 0x1>(p, tq + we.x, acc);
+        p = tq + ws.y; run_add<PB, 0x2>(p, tq + we.y, acc);
+        p = tq + ws.z; run_add<PB, 0x4>(p, tq + we.z, acc);
+        p = tq + ws.w; run_add<PB, 0x8>(p, tq + we.w, acc);
     }
 }
 
@@ -192,8 +243,10 @@ k_line(const LineArgs a)
     constexpr int Dc = 4 * LP;
     constexpr int TEAMS = kLineThreads / LP;
     const int tid = threadIdx.x, team = tid / LP, q = tid % LP;
-    const int ln = VERT ? blockIdx.x : blockIdx.y;
-    const int seg = VERT ? blockIdx.y : blockIdx.x;
+    // segments of one line are consecutive CTAs in both orientations: the halo a segment shares with its
+    // neighbour is re-read while it is still in L2
+    const int ln = blockIdx.y;
+    const int seg = blockIdx.x;
     const int vslot = blockIdx.z / a.nchunks, chunk = blockIdx.z % a.nchunks;
     const int W = a.W;
     const int LEN = VERT ? a.H : W;
@@ -204,20 +257,27 @@ k_line(const LineArgs a)
     const int d0 = chunk * Dc;
 
     float4 *C4 = reinterpret_cast<float4 *>(smem_raw);
-    uint32_t *sSE = reinterpret_cast<uint32_t *>(C4 + (size_t)P4 * LP);
+    uint32_t *sS = reinterpret_cast<uint32_t *>(C4 + (size_t)P4 * LP);
+    uint32_t *sE = sS + a.S;
+    constexpr uint32_t PB = LP * 16;  // bytes per tile position
 
-    // windows of this segment's outputs, in tile positions: [o + halo - A, o + halo + B)
+    // windows of this segment's outputs as byte offsets into the tile: [o + halo - A, o + halo + B) * PB.
+    // Slots past the line end inside the last group of four shadow that group's first output (summed,
+    // never stored), so the sum loops need no special case.
     {
         const uint32_t *__restrict__ arms = a.arms[vslot];
         for (int o = tid; o < a.S; o += kLineThreads) {
-            uint32_t se = 0;
-            if (o < Sact) {
-                const int t = t0 + o;
+            const int oe = o < Sact ? o : (o & ~3);
+            uint32_t ws = 0, we = 0;
+            if (oe < Sact) {
+                const int t = t0 + oe;
                 const uint32_t ar = __ldg(arms + (VERT ? (size_t)t * W + ln : (size_t)ln * W + t));
                 const int A = VERT ? arm_up(ar) : arm_left(ar), B = VERT ? arm_down(ar) : arm_right(ar);
-                se = (uint32_t)(o + halo - A) | ((uint32_t)(o + halo + B) << 16);
+                ws = (uint32_t)(oe + halo - A) * PB;
+                we = (uint32_t)(oe + halo + B) * PB;
             }
-            sSE[o] = se;
+            sS[o] = ws;
+            sE[o] = we;
         }
     }
 
@@ -227,7 +287,7 @@ k_line(const LineArgs a)
 
     if (MODE == LM_CI_H) {
         const int view = a.view_first + vslot;
-        uint32_t *sOwnP = sSE + a.S, *sOwnC = sOwnP + P4;
+        uint32_t *sOwnP = sE + a.S, *sOwnC = sOwnP + P4;
         const int NO = P4 + Dc;
         uint32_t *sOthP = sOwnC + P4, *sOthC = sOthP + NO;
         float *sLutCen = reinterpret_cast<float *>(sOthC + NO);
@@ -291,44 +351,80 @@ k_line(const LineArgs a)
         }
     } else {
         // tile <- volume, 16 B per cp.async; positions outside the line are never inside a window
-        const float4 *__restrict__ src = a.in[vslot] + line_base4;
-        for (int p = team; p < P; p += TEAMS) {
-            const int t = t0 - halo + p;
-            if (t >= 0 && t < LEN) cp_async16(&C4[(size_t)p * LP + q], src + (size_t)t * pos_stride4);
-        }
+        const int p_lo = max(0, halo - t0), p_hi = min(P, LEN - t0 + halo);
+        const long long step = (long long)TEAMS * (long long)pos_stride4 * 16;
+        const char *srcp = reinterpret_cast<const char *>(a.in[vslot] + line_base4) +
+                           (long long)(t0 - halo + team) * (long long)pos_stride4 * 16;
+        uint32_t sdst = smem_u32(C4) + (uint32_t)(team * LP + q) * 16u;
+        for (int p = team; p < P; p += TEAMS, srcp += step, sdst += TEAMS * PB)
+            if ((unsigned)(p - p_lo) < (unsigned)(p_hi - p_lo))
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(srcp) : "memory");
         cp_async_commit();
         cp_async_wait<0>();
     }
     __syncthreads();
 
     const int ngroups = (Sact + 3) >> 2;
+    const bool full_d = d0 + Dc <= a.D;  // no padded disparities in this chunk
     const int niter = (ngroups + TEAMS - 1) / TEAMS;
-    const float4 *base = C4 + q;
-    for (int it = 0; it < niter; ++it) {
-        const int g = it * TEAMS + team;
+    const uint32_t tq = smem_u32(C4) + (uint32_t)q * 16u;
+    const uint32_t *pS = sS + 4 * team;
+    const long long ostride = (long long)pos_stride4 * 16;  // bytes between consecutive outputs of the line
+    char *dstp = nullptr;
+    if (MODE != LM_H_WTA)
+        dstp = reinterpret_cast<char *>(a.out[vslot] + line_base4) + (long long)(t0 + 4 * team) * ostride;
+    for (int it = 0, g = team; it < niter; ++it, g += TEAMS, pS += 4 * TEAMS, dstp += 4 * TEAMS * ostride) {
         const bool active = g < ngroups;
-        uint32_t se[4] = {0u, 0u, 0u, 0u};
+        uint4 ws = make_uint4(0u, 0u, 0u, 0u), we = ws;
         if (active) {
-            const uint4 w = *reinterpret_cast<const uint4 *>(sSE + 4 * g);
-            se[0] = w.x; se[1] = w.y; se[2] = w.z; se[3] = w.w;
-#pragma unroll
-            for (int i = 1; i < 4; ++i)
-                if (4 * g + i >= Sact) se[i] = se[0];  // past the line end: shadow output 0, never stored
+            ws = *reinterpret_cast<const uint4 *>(pS);
+            we = *reinterpret_cast<const uint4 *>(pS + a.S);
         }
         float4 acc[4];
-        sum_group4<LP>(base, se, acc);
+        sum_group4<LP>(tq, ws, we, acc);
 
         if (MODE != LM_H_WTA) {
             if (active) {
-                float4 *__restrict__ dst = a.out[vslot] + line_base4 + (size_t)(t0 + 4 * g) * pos_stride4;
+                const int rem = Sact - 4 * g;
+                if (rem >= 4) {
+                    *reinterpret_cast<float4 *>(dstp) = acc[0];
+                    *reinterpret_cast<float4 *>(dstp + ostride) = acc[1];
+                    *reinterpret_cast<float4 *>(dstp + 2 * ostride) = acc[2];
+                    *reinterpret_cast<float4 *>(dstp + 3 * ostride) = acc[3];
+                } else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (4 * g + i < Sact) dst[(size_t)i * pos_stride4] = acc[i];
+                    for (int i = 0; i < 3; ++i)
+                        if (i < rem) *reinterpret_cast<float4 *>(dstp + i * ostride) = acc[i];
+                }
             }
         } else {
             // dc_wta_kernel (d_dc_wta.cu:9-35): strict '>' from FLT_MAX, first minimum wins.
-            // Aggregated ADCensus costs are >= 0, so their bit patterns order like the floats.
+            // Aggregated ADCensus costs are >= +0, so their bit patterns order like the floats.
             const int dq = d0 + 4 * q;
+            if (LP == 32 && full_d) {
+                // One warp = one pixel, no padded disparities.  Lane minimum (two integer min instructions),
+                // CREDUX.MIN across the warp; the lowest lane holding the minimum owns the lowest winning
+                // disparity, finds which of its four it was and stores: no shuffles, no per-disparity selects.
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t bx = __float_as_uint(acc[i].x), by = __float_as_uint(acc[i].y),
+                                   bz = __float_as_uint(acc[i].z), bw = __float_as_uint(acc[i].w);
+                    const uint32_t lm = min(min(bx, by), min(bz, bw));
+                    const uint32_t m = __reduce_min_sync(0xffffffffu, lm);
+                    const uint32_t who = __ballot_sync(0xffffffffu, lm == m);
+                    if (active && q == __ffs(who) - 1 && 4 * g + i < Sact) {
+                        const int j = bx == m ? 0 : (by == m ? 1 : (bz == m ? 2 : 3));
+                        const size_t pix = (size_t)ln * W + (t0 + 4 * g + i);
+                        if (a.nchunks == 1) {
+                            a.disp[vslot][pix] = (float)(dq + j) - (float)a.zd;
+                        } else {
+                            const unsigned long long key =
+                                ((unsigned long long)float_orderable(__uint_as_float(m)) << 32) | (uint32_t)(dq + j);
+                            atomicMin(a.wta_key[vslot] + pix, key);
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float best = FLT_MAX;
@@ -365,6 +461,7 @@ k_line(const LineArgs a)
                         atomicMin(a.wta_key[vslot] + pix, key);
                     }
                 }
+            }
             }
         }
     }

@@ -567,7 +567,7 @@ static int launch_aggregate(s2mv_ctx *c, LineArgs a, float4 *A, float4 *B, size_
     const CostPlan &pl = c->plan;
     const int H = a.H, W = a.W;
     const dim3 gh((W + pl.S_h - 1) / pl.S_h, H, nviews * pl.nchunks);
-    const dim3 gv(W, (H + pl.S_v - 1) / pl.S_v, nviews * pl.nchunks);
+    const dim3 gv((H + pl.S_v - 1) / pl.S_v, W, nviews * pl.nchunks);
     // pass 1: (CI ->) H : . -> A      [stage API: B -> A is not needed; input planes are loaded into B]
     a.S = pl.S_h;
     for (int v = 0; v < nviews; ++v) { a.in[v] = B + v * view_stride4; a.out[v] = A + v * view_stride4; }
