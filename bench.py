@@ -17,10 +17,12 @@ parameters.  With N GPUs every rank processes its own K frames of the stream
   value   frames/s with the input frame already resident in HBM (CUDA events
           around s2mv_process_sbs_device, summed over the K steps, max over
           ranks); L2 is flushed (256 MB write) between steps, untimed.
-  e2e     frames/s through the host-buffer C-ABI call s2mv_process_sbs (the
-          adcensus_stm contract): pinned host frame -> H2D, all kernels, D2H
-          of both disparity maps and the interlaced frame, inside the timed
-          region every step.
+  e2e     frames/s through the host-buffer C ABI, H2D of the frame and D2H of
+          both disparity maps and the interlaced frame inside the timed region
+          every step: the asynchronous frame stream (s2mv_stream_submit /
+          s2mv_stream_collect, 3 frames in flight: copies overlap kernels), with
+          the synchronous adcensus_stm-contract call (s2mv_process_sbs) reported
+          beside it as e2e.synchronous_call.
   roofline  for the slowest cost-volume kernel: algorithmic bytes per launch
           (stage-separable model of BASELINE.md §3: 40 B per disparity
           evaluation = 20 V per frame, split 6 V / 4 V / 4 V / 6 V over the four
@@ -228,11 +230,39 @@ def main():
     for _ in range(K):
         pipe.adcensus_stm_into(np_in, np_dl, np_dr, np_out)   # synchronous: returns after the D2H copies
     torch.cuda.synchronize()
+    e2e_sync_s = time.perf_counter() - t0
+    sharding.barrier()
+    e2e_sync_fps, _, _ = sharding.aggregate_throughput(K, e2e_sync_s, dev)
+    assert np.array_equal(np_out, d_out.cpu().numpy()), "host and device entry points disagree"
+
+    # ---- end to end through the asynchronous frame stream (the video loop) ----
+    # every frame: host frame -> the slot's pinned buffer -> H2D -> all kernels -> D2H of both disparity
+    # maps and the interlaced frame into pinned host memory; copies of neighbouring frames overlap the kernels
+    DEPTH = 3
+    pipe.stream_open(DEPTH)
+
+    def stream_run(n):
+        got = None
+        for _ in range(n):
+            if pipe.stream_pending == DEPTH:
+                got = pipe.stream_collect(copy=False)
+            np.copyto(pipe.stream_input_buffer(), np_in)   # stands in for the decoder writing the frame
+            pipe.stream_submit(None)
+        while pipe.stream_pending:
+            got = pipe.stream_collect(copy=False)
+        return got
+
+    stream_run(Wm)
+    sharding.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    got = stream_run(K)
     e2e_s = time.perf_counter() - t0
     sharding.barrier()
     clocks = sampler.stop()
     e2e_fps, _, _ = sharding.aggregate_throughput(K, e2e_s, dev)
-    assert np.array_equal(np_out, d_out.cpu().numpy()), "host and device entry points disagree"
+    assert np.array_equal(got[2], np_out) and np.array_equal(got[0], np_dl), "stream and synchronous entry points disagree"
+    pipe.stream_close()
 
     if rank != 0:
         return 0
@@ -252,8 +282,8 @@ def main():
         pass
     costvol_ms = (stage_ms["prepare"] + stage_ms["costvol"]) / K
     de = 2.0 * W * H * D
-    roofline = {"bound": "hbm", "kernel": {"ci_h1": "k_hpass<CI,sum,store>", "v2": "k_vpass (pass 2)",
-                                           "v3": "k_vpass (pass 3)", "h4_wta": "k_hpass<load,sum,WTA>"}[dom],
+    roofline = {"bound": "hbm", "kernel": {"ci_h1": "k_line<LM_CI_H> (cost init + H pass 1)", "v2": "k_line<LM_V> (V pass 2)",
+                                           "v3": "k_line<LM_V> (V pass 3)", "h4_wta": "k_line<LM_H_WTA> (H pass 4 + WTA)"}[dom],
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": dom_ms,
                 "costvol_leg": {"ms": costvol_ms, "mde_per_s": de / (costvol_ms * 1e-3) / 1e6,
@@ -273,7 +303,9 @@ def main():
         "config": {"workload": WORKLOAD, "parallelism": f"frame-parallel x{world}, no collectives",
                    "l2": "256 MB flush write between timed steps; per-frame volume traffic >> L2"},
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(sbs.nbytes),
-                "d2h_bytes_per_step": int(np_dl.nbytes + np_dr.nbytes + np_out.nbytes)},
+                "d2h_bytes_per_step": int(np_dl.nbytes + np_dr.nbytes + np_out.nbytes),
+                "api": f"s2mv_stream_submit/collect, {DEPTH} frames in flight (host frame -> pinned slot -> H2D -> kernels -> D2H)",
+                "synchronous_call": {"value": e2e_sync_fps, "unit": "frames/s", "api": "s2mv_process_sbs (adcensus_stm contract)"}},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,

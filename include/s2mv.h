@@ -94,6 +94,27 @@ int s2mv_costvol_device(s2mv_ctx *ctx, const uint8_t *d_img_sbs, int num_cols_sb
 
 int s2mv_synchronize(s2mv_ctx *ctx);
 
+/* ---- asynchronous frame stream (the video loop, video_io.cpp:139-160) -----
+ * The same frames through the same kernels as s2mv_process_sbs, with the host
+ * <-> device copies (d_io.cu:43-44,153-154,205) taken off the critical path:
+ * `depth` slots of pinned host + device in/out buffers, H2D of frame i+1 and
+ * D2H of frame i-1 overlap the kernels of frame i.  Frames come back in
+ * submission order.  submit fails (S2MV_ERR_BAD_PARAM) when all slots are in
+ * flight; collect blocks until the oldest frame's outputs are on the host.
+ *   s2mv_stream_input_buffer: the pinned input buffer the NEXT submit will
+ *     use, so a decoder can write into it directly; then submit(ctx, NULL).
+ *   s2mv_stream_collect: copies into disp_l/disp_r/interlaced when non-NULL
+ *     and/or returns the slot's pinned output buffers (valid until `depth`
+ *     further submits). */
+int s2mv_stream_open(s2mv_ctx *ctx, int depth, int num_cols_sbs);
+int s2mv_stream_input_buffer(s2mv_ctx *ctx, uint8_t **pinned_img_sbs);
+int s2mv_stream_submit(s2mv_ctx *ctx, const uint8_t *img_sbs);
+int s2mv_stream_collect(s2mv_ctx *ctx, float *disp_l, float *disp_r, uint8_t *interlaced,
+                        const float **pinned_disp_l, const float **pinned_disp_r,
+                        const uint8_t **pinned_interlaced);
+int s2mv_stream_pending(const s2mv_ctx *ctx);
+int s2mv_stream_close(s2mv_ctx *ctx);
+
 /* Device-event timing of the last s2mv_process_sbs* call, in milliseconds:
  * [0] prepare (demux, gray, census, arms)  [1] cost volume (CI+CA+WTA)
  * [2] refinement (DCC, IRV, bilateral)     [3] DIBR + interlace

@@ -26,6 +26,8 @@ EXPORTED_SYMBOLS = [
     "s2mv_ca_cross", "s2mv_dc_wta", "s2mv_dr_dcc", "s2mv_dr_irv", "s2mv_filter_bilateral_1",
     "s2mv_dibr_occl", "s2mv_filter_bleed_1", "s2mv_dibr_occl_to_mask", "s2mv_filter_gaussian_1",
     "s2mv_dibr_dbm", "s2mv_mux_multiview",
+    "s2mv_stream_open", "s2mv_stream_input_buffer", "s2mv_stream_submit", "s2mv_stream_collect",
+    "s2mv_stream_pending", "s2mv_stream_close",
 ]
 # the reference's own C++ symbols exported as shims (include/s2mv_compat.h)
 COMPAT_SYMBOLS = [
@@ -122,6 +124,7 @@ class Pipeline:
         self._ctx = C.c_void_p()
         _check(self._L.s2mv_create(C.byref(self._ctx), int(device)))
         self.params = None
+        self._stream_cols = None
         if params:
             self.configure(**params)
 
@@ -232,6 +235,47 @@ class Pipeline:
     def costvol_device(self, d_sbs_ptr, num_cols_sbs, d_disp_l=0, d_disp_r=0, stream=None):
         _check(self._L.s2mv_costvol_device(self._ctx, C.c_void_p(d_sbs_ptr), int(num_cols_sbs),
                                            C.c_void_p(d_disp_l), C.c_void_p(d_disp_r), self._stream(stream)))
+
+    # ---- asynchronous frame stream (video loop) ---------------------------
+    def stream_open(self, depth=3, num_cols_sbs=None):
+        """Open `depth` in-flight slots; frames then go submit() ... collect() in order."""
+        ncs = 2 * self.params.num_cols if num_cols_sbs is None else int(num_cols_sbs)
+        _check(self._L.s2mv_stream_open(self._ctx, int(depth), ncs))
+        self._stream_cols = ncs
+
+    def stream_close(self):
+        _check(self._L.s2mv_stream_close(self._ctx))
+
+    @property
+    def stream_pending(self):
+        return self._L.s2mv_stream_pending(self._ctx)
+
+    def stream_input_buffer(self):
+        """numpy view of the pinned buffer the next submit() will upload (decode straight into it)."""
+        ptr = C.POINTER(C.c_uint8)()
+        _check(self._L.s2mv_stream_input_buffer(self._ctx, C.byref(ptr)))
+        p = self.params
+        return np.ctypeslib.as_array(ptr, shape=(p.num_rows, self._stream_cols, 3))
+
+    def stream_submit(self, img_sbs=None):
+        """Enqueue one frame (None: the buffer from stream_input_buffer() is already filled)."""
+        if img_sbs is not None:
+            img_sbs = np.ascontiguousarray(img_sbs, np.uint8)
+            if self._stream_cols is not None and img_sbs.shape != (self.params.num_rows, self._stream_cols, 3):
+                raise S2mvError("frame shape does not match the opened stream")
+        _check(self._L.s2mv_stream_submit(self._ctx, _p(img_sbs)))
+
+    def stream_collect(self, copy=True):
+        """Oldest in-flight frame -> (disp_l, disp_r, interlaced).  copy=False returns views of the slot's
+        pinned buffers (valid until `depth` further submits)."""
+        p = self.params
+        H, W = p.num_rows, p.num_cols
+        pl, pr, po = C.POINTER(C.c_float)(), C.POINTER(C.c_float)(), C.POINTER(C.c_uint8)()
+        _check(self._L.s2mv_stream_collect(self._ctx, None, None, None, C.byref(pl), C.byref(pr), C.byref(po)))
+        dl = np.ctypeslib.as_array(pl, shape=(H, W))
+        dr = np.ctypeslib.as_array(pr, shape=(H, W))
+        out = np.ctypeslib.as_array(po, shape=(p.num_rows_out, p.num_cols_out, 3))
+        return (dl.copy(), dr.copy(), out.copy()) if copy else (dl, dr, out)
 
     def read_taps(self):
         p = self.params

@@ -56,6 +56,7 @@ struct LineArgs {
     int S;        // outputs per CTA along the line (multiple of 4)
     int halo;     // usd
     int view_first;
+    int ln_first;  // first line of this launch (column strips of the vertical passes)
 };
 
 // shared-memory bytes of one CTA
@@ -245,7 +246,7 @@ k_line(const LineArgs a)
     const int tid = threadIdx.x, team = tid / LP, q = tid % LP;
     // segments of one line are consecutive CTAs in both orientations: the halo a segment shares with its
     // neighbour is re-read while it is still in L2
-    const int ln = blockIdx.y;
+    const int ln = a.ln_first + blockIdx.y;
     const int seg = blockIdx.x;
     const int vslot = blockIdx.z / a.nchunks, chunk = blockIdx.z % a.nchunks;
     const int W = a.W;

@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../include/s2mv.h"
@@ -241,7 +242,18 @@ struct s2mv_ctx {
     cudaEvent_t kev[5] = {};  // around the four cost-volume kernels
     int launches = 0;
     float y_interval = 0.f;
+    // asynchronous frame stream (s2mv_stream.inl)
+    struct StreamSlot {
+        uint8_t *d_sbs = nullptr, *d_out = nullptr, *h_sbs = nullptr, *h_out = nullptr;
+        float *d_disp[2] = {}, *h_disp[2] = {};
+        cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+        bool busy = false;
+    };
+    std::vector<StreamSlot> slots;
+    cudaStream_t st_in = nullptr, st_out = nullptr;
+    int stream_cols_sbs = 0, slot_head = 0, slot_tail = 0, slots_pending = 0;
 };
+static void stream_release(s2mv_ctx *c);
 
 static int dev_alloc(s2mv_ctx *c, void **p, size_t bytes)
 {
@@ -256,6 +268,7 @@ static int dev_alloc_t(s2mv_ctx *c, T **p, size_t count) { return dev_alloc(c, (
 
 static void free_arena(s2mv_ctx *c)
 {
+    stream_release(c);
     for (void *p : c->allocs) cudaFree(p);
     c->allocs.clear();
     c->arena_bytes = 0;
@@ -999,3 +1012,4 @@ extern "C" int s2mv_read_taps(s2mv_ctx *c, float *wta_l, float *wta_r, uint8_t *
 }
 
 #include "s2mv_stages.inl"
+#include "s2mv_stream.inl"

@@ -160,3 +160,41 @@ def test_config3_1080p_full_frame_properties(pipe, oracle):
     il, _ = oracle.irv(taps["wta_l"], ol, taps["arms_l"], 20, 0.4, D, zd, 17, 5)
     assert np.array_equal(il, taps["irv_l"])
     assert np.array_equal(oracle.bilateral(il, 7, 5.0, 10.0, D), a[0])
+
+
+@pytest.mark.gpu
+def test_frame_stream_matches_synchronous_call():
+    """s2mv_stream_*: same frames, same order, same bytes as s2mv_process_sbs; error behaviour of a full /
+    empty stream."""
+    import s2mv_b200
+    from s2mv_b200_pkg import synth
+    H, W, D, zd = 96, 320, 32, 16
+    frames = [synth.make_sbs(H, W, 100 + i) for i in range(7)]
+    with s2mv_b200.Pipeline(0, num_rows=H, num_cols=W, num_disp=D, zero_disp=zd, num_views=8, angle=18, **ALGO) as p:
+        want = [p.adcensus_stm(f) for f in frames]
+        with pytest.raises(s2mv_b200.S2mvError):
+            p.stream_submit(frames[0])          # not opened
+        p.stream_open(3)
+        with pytest.raises(s2mv_b200.S2mvError):
+            p.stream_collect()                  # nothing in flight
+        got = []
+        for i, f in enumerate(frames):
+            if p.stream_pending == 3:
+                got.append(p.stream_collect())
+            if i % 2:
+                np.copyto(p.stream_input_buffer(), f)
+                p.stream_submit(None)
+            else:
+                p.stream_submit(f)
+        assert p.stream_pending == 3
+        with pytest.raises(s2mv_b200.S2mvError):
+            p.stream_submit(frames[0])          # all slots in flight
+        while p.stream_pending:
+            got.append(p.stream_collect())
+        p.stream_close()
+        assert len(got) == len(frames)
+        for (dl, dr, out), (wl, wr, wo) in zip(got, want):
+            assert np.array_equal(dl, wl) and np.array_equal(dr, wr) and np.array_equal(out, wo)
+        # the synchronous call still works after the stream is closed
+        dl, dr, out = p.adcensus_stm(frames[0])
+        assert np.array_equal(out, want[0][2])
