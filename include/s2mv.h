@@ -71,6 +71,15 @@ int s2mv_create(s2mv_ctx **ctx, int device);
 void s2mv_destroy(s2mv_ctx *ctx);
 int s2mv_configure(s2mv_ctx *ctx, const s2mv_params *p);
 size_t s2mv_arena_bytes(const s2mv_ctx *ctx);
+/* num_disp > 128: the four aggregation passes are independent per disparity,
+ * so the arena can hold ONE 128-disparity chunk of both volumes and run the
+ * chunks one after another (winner-takes-all merges through 64-bit keys)
+ * instead of holding num_disp-deep volumes: 8K D=512 needs 68 GB instead of
+ * 272 GB.  mode -1 (default): chosen at s2mv_configure when the full volumes
+ * do not fit the device; 0: never; 1: whenever num_disp > 128.  Call before
+ * s2mv_configure.  Results are identical in both layouts. */
+int s2mv_set_chunk_sequential(s2mv_ctx *ctx, int mode);
+int s2mv_is_chunk_sequential(const s2mv_ctx *ctx);
 int s2mv_device_sm_count(const s2mv_ctx *ctx);
 
 /* ---- frame entry points (replace adcensus_stm, d_io.cu:7-238) ---------- */

@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "s2mv_dibr_occl", "s2mv_filter_bleed_1", "s2mv_dibr_occl_to_mask", "s2mv_filter_gaussian_1",
     "s2mv_dibr_dbm", "s2mv_mux_multiview",
     "s2mv_stream_open", "s2mv_stream_input_buffer", "s2mv_stream_submit", "s2mv_stream_collect",
-    "s2mv_stream_pending", "s2mv_stream_close",
+    "s2mv_stream_pending", "s2mv_stream_close", "s2mv_set_chunk_sequential", "s2mv_is_chunk_sequential",
 ]
 # the reference's own C++ symbols exported as shims (include/s2mv_compat.h)
 COMPAT_SYMBOLS = [
@@ -151,6 +151,15 @@ class Pipeline:
         _check(self._L.s2mv_configure(self._ctx, C.byref(p)))
         self.params = p
         return self
+
+    def set_chunk_sequential(self, mode):
+        """-1 auto / 0 never / 1 always (num_disp > 128): one 128-disparity chunk of the volumes resident at a
+        time.  Takes effect at the next configure()."""
+        _check(self._L.s2mv_set_chunk_sequential(self._ctx, int(mode)))
+
+    @property
+    def chunk_sequential(self):
+        return bool(self._L.s2mv_is_chunk_sequential(self._ctx))
 
     @property
     def arena_bytes(self):

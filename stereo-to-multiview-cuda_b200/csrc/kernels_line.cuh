@@ -57,6 +57,8 @@ struct LineArgs {
     int halo;     // usd
     int view_first;
     int ln_first;  // first line of this launch (column strips of the vertical passes)
+    int d_first;   // disparity of chunk 0 of this launch (chunk-sequential mode: one 128-disparity chunk per launch)
+    int use_keys;  // WTA through 64-bit (cost, d) atomicMin keys: the disparity range spans several chunks/launches
 };
 
 // shared-memory bytes of one CTA
@@ -255,7 +257,7 @@ k_line(const LineArgs a)
     const int Sact = min(a.S, LEN - t0);
     const int halo = a.halo;
     const int P = a.S + 2 * halo, P4 = (P + 3) & ~3;
-    const int d0 = chunk * Dc;
+    const int d0 = a.d_first + chunk * Dc;
 
     float4 *C4 = reinterpret_cast<float4 *>(smem_raw);
     uint32_t *sS = reinterpret_cast<uint32_t *>(C4 + (size_t)P4 * LP);
@@ -416,7 +418,7 @@ k_line(const LineArgs a)
                     if (active && q == __ffs(who) - 1 && 4 * g + i < Sact) {
                         const int j = bx == m ? 0 : (by == m ? 1 : (bz == m ? 2 : 3));
                         const size_t pix = (size_t)ln * W + (t0 + 4 * g + i);
-                        if (a.nchunks == 1) {
+                        if (!a.use_keys) {
                             a.disp[vslot][pix] = (float)(dq + j) - (float)a.zd;
                         } else {
                             const unsigned long long key =
@@ -454,7 +456,7 @@ k_line(const LineArgs a)
                 if (active && q == 0 && 4 * g + i < Sact) {
                     if (bestd == 0x7fffffff) bestd = 0;
                     const size_t pix = (size_t)ln * W + (t0 + 4 * g + i);
-                    if (a.nchunks == 1) {
+                    if (!a.use_keys) {
                         a.disp[vslot][pix] = (float)bestd - (float)a.zd;
                     } else {
                         const unsigned long long key =

@@ -116,6 +116,7 @@ static void host_gaussian_1d(std::vector<float> &k, int size, float sigma)
 // ------------------------------------------------------------ cost plan
 struct CostPlan {
     int D, Dp, LP, LPtot, nchunks, usd, M, S_ci;
+    bool chunk_seq;                     // volumes hold ONE 128-disparity chunk; chunks run one after another
     size_t smem_ci;                     // CI-only stage kernels (k_hpass)
     int S_h, S_v;                       // outputs per CTA along a row / a column (k_line)
     size_t smem_line_ci, smem_line_h, smem_line_v;
@@ -187,6 +188,7 @@ static int make_plan(CostPlan &pl, int H, int W, int D, int zd, int usd, int sm_
         pl.LP = 32;
     }
     pl.LPtot = pl.Dp / 4;
+    pl.chunk_seq = false;
     pl.M = zd > D - 1 - zd ? zd : D - 1 - zd;
     if (pl.M < 0) pl.M = 0;
     pl.S_ci = pick_segment(W, usd, 4 * pl.LP, pl.M, true, pl.LP, &pl.smem_ci);
@@ -208,6 +210,7 @@ struct s2mv_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
     bool configured = false, timing = false, taps = false;
+    int chunk_seq_mode = -1;  // -1 auto (when the full volumes do not fit), 0 never, 1 whenever D > 128
     s2mv_params prm;
     CostPlan plan;
     size_t arena_bytes = 0;
@@ -425,7 +428,21 @@ extern "C" int s2mv_configure(s2mv_ctx *c, const s2mv_params *p)
     c->plan = pl;
     c->lut_ad_coeff = c->lut_cen_coeff = -1.f;
     const size_t n = (size_t)p->num_rows * p->num_cols;
-    const size_t vol_elems = 2 * n * pl.Dp;
+    if (pl.nchunks > 1) {
+        // D > 128: the four passes are independent per disparity, so the volumes only ever need one
+        // 128-disparity chunk when chunks run one after another (WTA merges through 64-bit keys).
+        // Chosen automatically when two full ping-pong volumes would not fit the device.
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const double full = 2.0 * 2.0 * (double)n * pl.Dp * sizeof(float);
+        const bool want = c->chunk_seq_mode == 1 || (c->chunk_seq_mode < 0 && full > 0.85 * (double)free_b);
+        if (want) {
+            pl.chunk_seq = true;
+            pl.LPtot = pl.LP;  // volume rows hold one chunk
+            c->plan = pl;
+        }
+    }
+    const size_t vol_elems = 2 * n * (pl.chunk_seq ? 4 * pl.LP : pl.Dp);
     for (int v = 0; v < 2; ++v) {
         TRY(dev_alloc_t(c, &c->pix[v], n));
         TRY(dev_alloc_t(c, &c->cen[v], n));
@@ -471,6 +488,15 @@ extern "C" int s2mv_configure(s2mv_ctx *c, const s2mv_params *p)
     c->configured = true;
     return S2MV_OK;
 }
+
+extern "C" int s2mv_set_chunk_sequential(s2mv_ctx *c, int mode)
+{
+    if (!c) return fail(S2MV_ERR_BAD_PARAM, "null ctx");
+    if (mode < -1 || mode > 1) return fail(S2MV_ERR_BAD_PARAM, "mode must be -1 (auto), 0 or 1");
+    c->chunk_seq_mode = mode;
+    return S2MV_OK;
+}
+extern "C" int s2mv_is_chunk_sequential(const s2mv_ctx *c) { return c && c->configured && c->plan.chunk_seq ? 1 : 0; }
 
 extern "C" int s2mv_enable_timing(s2mv_ctx *c, int on)
 {
@@ -567,7 +593,8 @@ static void fill_largs(const s2mv_ctx *c, LineArgs &a, int H, int W, int zd, flo
     a.lutAd = c->lutAd; a.lutCen = c->lutCen;
     a.inv_ad = (float)(1.0 / ad_coeff);  // d_ci_adcensus.cu:160 (see build_luts)
     a.H = H; a.W = W; a.D = pl.D; a.zd = zd;
-    a.LPtot = pl.LPtot; a.nchunks = pl.nchunks;
+    a.LPtot = pl.LPtot; a.nchunks = pl.chunk_seq ? 1 : pl.nchunks;
+    a.use_keys = pl.nchunks > 1;
     a.halo = pl.usd; a.view_first = 0;
 }
 
@@ -579,8 +606,8 @@ static int launch_aggregate(s2mv_ctx *c, LineArgs a, float4 *A, float4 *B, size_
 {
     const CostPlan &pl = c->plan;
     const int H = a.H, W = a.W;
-    const dim3 gh((W + pl.S_h - 1) / pl.S_h, H, nviews * pl.nchunks);
-    const dim3 gv((H + pl.S_v - 1) / pl.S_v, W, nviews * pl.nchunks);
+    const dim3 gh((W + pl.S_h - 1) / pl.S_h, H, nviews * a.nchunks);
+    const dim3 gv((H + pl.S_v - 1) / pl.S_v, W, nviews * a.nchunks);
     // pass 1: (CI ->) H : . -> A      [stage API: B -> A is not needed; input planes are loaded into B]
     a.S = pl.S_h;
     for (int v = 0; v < nviews; ++v) { a.in[v] = B + v * view_stride4; a.out[v] = A + v * view_stride4; }
@@ -625,7 +652,14 @@ static int launch_costvol(s2mv_ctx *c, float *dispL, float *dispR, cudaStream_t 
     a.disp[0] = dispL; a.disp[1] = dispR;
     if (pl.nchunks > 1)
         for (int v = 0; v < 2; ++v) CU(cudaMemsetAsync(c->wta_key[v], 0xff, n * sizeof(unsigned long long), st));
-    TRY(launch_aggregate(c, a, A, B, view_stride4, 2, true, true, st));
+    if (pl.chunk_seq) {
+        for (int ch = 0; ch < pl.nchunks; ++ch) {
+            a.d_first = ch * 4 * pl.LP;
+            TRY(launch_aggregate(c, a, A, B, view_stride4, 2, true, true, st));
+        }
+    } else {
+        TRY(launch_aggregate(c, a, A, B, view_stride4, 2, true, true, st));
+    }
     if (pl.nchunks > 1) {
         k_wta_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->wta_key[0], dispL, p.zero_disp, n);
         k_wta_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->wta_key[1], dispR, p.zero_disp, n);

@@ -37,6 +37,15 @@ int acquire(s2mv_ctx *user, int H, int W, int D, int zd, int usd, s2mv_ctx **out
     return S2MV_OK;
 }
 
+// the stage entry points exchange whole cost volumes with the host: they need them resident
+int need_full_volume(const s2mv_ctx *c)
+{
+    if (c->plan.chunk_seq)
+        return fail(S2MV_ERR_OOM, "the full %d-disparity cost volumes do not fit this device (chunk-sequential arena); "
+                                  "the per-stage entry points need them resident", c->plan.D);
+    return S2MV_OK;
+}
+
 int upload(void *dst, const void *src, size_t bytes, cudaStream_t st)
 {
     CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
@@ -57,6 +66,7 @@ int stage_ci(s2mv_ctx *user, const uint8_t *img_l, const uint8_t *img_r, float *
     if (elem_sz != 3) return fail(S2MV_ERR_BAD_PARAM, "elem_sz must be 3");
     s2mv_ctx *c;
     TRY(acquire(user, H, W, D, zd, user && user->configured ? user->prm.usd : 17, &c));
+    TRY(need_full_volume(c));
     cudaStream_t st = c->stream;
     const size_t n = (size_t)H * W;
     const CostPlan &pl = c->plan;
@@ -156,6 +166,7 @@ extern "C" int s2mv_ca_cross(s2mv_ctx *ctx, const uint8_t *img, uint8_t **cross,
     if (elem_sz != 3) return fail(S2MV_ERR_BAD_PARAM, "elem_sz must be 3");
     s2mv_ctx *c;
     TRY(acquire(ctx, H, W, D, D / 2, usd, &c));  // zero_disp plays no part in aggregation
+    TRY(need_full_volume(c));
     cudaStream_t st = c->stream;
     const CostPlan &pl = c->plan;
     const size_t n = (size_t)H * W;

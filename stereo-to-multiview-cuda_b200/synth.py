@@ -36,12 +36,20 @@ def make_pair(height, width, seed, n_ellipses=40, noise_sigma=2.0, disp_lo=-24.0
         cx, cy = rng.uniform(0, width), rng.uniform(0, height)
         ax, ay = rng.uniform(0.03, 0.18, 2) * scale
         th = rng.uniform(0, np.pi)
-        dx, dy = xx - cx, yy - cy
+        # same ellipse test as on the full grid, evaluated inside its bounding box only
+        r = float(max(ax, ay)) + 1.0
+        x0, x1 = max(int(cx - r), 0), min(int(cx + r) + 2, width)
+        y0, y1 = max(int(cy - r), 0), min(int(cy + r) + 2, height)
+        colour = rng.uniform(20, 235, 3).astype(np.float32)
+        dval = rng.uniform(0.5 * (disp_lo + disp_hi), disp_hi)
+        if x0 >= x1 or y0 >= y1:
+            continue
+        dx, dy = xx[y0:y1, x0:x1] - cx, yy[y0:y1, x0:x1] - cy
         u = dx * np.cos(th) + dy * np.sin(th)
         v = -dx * np.sin(th) + dy * np.cos(th)
         m = (u / ax) ** 2 + (v / ay) ** 2 <= 1.0
-        img[m] = rng.uniform(20, 235, 3).astype(np.float32)
-        disp[m] = rng.uniform(0.5 * (disp_lo + disp_hi), disp_hi)
+        img[y0:y1, x0:x1][m] = colour
+        disp[y0:y1, x0:x1][m] = dval
     left = img + rng.normal(0, noise_sigma, img.shape).astype(np.float32)
     # right(x) = left(x + d): sample the clean image at shifted columns (nearest)
     src = np.clip(np.rint(xx + disp), 0, width - 1).astype(np.int64)

@@ -80,6 +80,28 @@ def test_d256_multi_chunk_wta(pipe, oracle):
     assert_frame_equal(got, want)
 
 
+@pytest.mark.parametrize("D,zd", [(256, 128), (200, 90), (300, 0)])
+def test_chunk_sequential_volumes_match_resident_volumes(s2mv, oracle, D, zd):
+    # num_disp > 128 with ONE 128-disparity chunk of the volumes resident at a time (what 8K D=512 needs on
+    # one GPU): the same frame bit for bit as the fully resident layout and as the oracle; the stage entry
+    # points that exchange whole volumes refuse to run on such an arena
+    from s2mv_b200_pkg import synth
+    sbs = synth.make_sbs(40, 336, 4100 + D)
+    with s2mv.Pipeline(0) as p:
+        p.set_chunk_sequential(1)
+        got, want = run_both(p, oracle, sbs, 336, D, zd)
+        assert p.chunk_sequential
+        seq_bytes = p.arena_bytes
+        assert_frame_equal(got, want)
+        img = np.ascontiguousarray(sbs[:, :336])
+        with pytest.raises(s2mv.S2mvError):
+            p.ci_adcensus(img, img, 10.0, 30.0, D, zd)
+        p.set_chunk_sequential(0)
+        got2, _ = run_both(p, oracle, sbs, 336, D, zd)
+        assert not p.chunk_sequential and p.arena_bytes > seq_bytes
+        assert_frame_equal(got2, want)
+
+
 def test_device_entry_points_match_host_entry(pipe, bud_sbs):
     import torch
     H, W = 384, 640
