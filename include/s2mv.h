@@ -103,6 +103,38 @@ int s2mv_costvol_device(s2mv_ctx *ctx, const uint8_t *d_img_sbs, int num_cols_sb
 
 int s2mv_synchronize(s2mv_ctx *ctx);
 
+/* ---- row-band mode: ONE frame over several contexts / GPUs ----------------
+ * The reference has no multi-GPU path; this is the single-large-frame split
+ * of SURVEY §8(e).  Each context owns the contiguous rows [band_y0, band_y1)
+ * of the frame described by `frame` and works on a sub-image = those rows plus
+ * `apron` rows either side (0 = default, >= 6*usd + 18).  The cheap O(W*H)
+ * stages run on the sub-image as if it were a whole image (exact on the own
+ * rows); the cost-volume passes run on the own rows only and the usd volume
+ * rows either side that the vertical passes read are exchanged between
+ * neighbouring bands by the caller (cudaMemcpyPeerAsync / NCCL send-recv):
+ *
+ *   s2mv_band_prepare(frame)           demux, gray, census, arms of the sub-image
+ *   s2mv_band_pass(1)                  cost init + horizontal pass     -> volume A
+ *   exchange s2mv_band_halo(1, ...)    up/down, both views
+ *   s2mv_band_pass(2)                  vertical pass                   -> volume B
+ *   exchange s2mv_band_halo(2, ...)
+ *   s2mv_band_pass(3); s2mv_band_pass(4)   vertical; horizontal + WTA  -> own rows of s2mv_band_disp()
+ *   fill the other rows of s2mv_band_disp() planes from the other bands
+ *   s2mv_band_finish()                 refinement + DIBR + interlace, own rows out
+ *
+ * Results equal the single-context frame bit for bit (tests/test_gpu_rowband.py).
+ * All pointers are DEVICE pointers; every call is asynchronous on `stream`
+ * (NULL = the context's stream).  Requires output size == input size. */
+int s2mv_configure_band(s2mv_ctx *ctx, const s2mv_params *frame, int band_y0, int band_y1, int apron);
+int s2mv_band_info(const s2mv_ctx *ctx, int *local_y0, int *local_rows, int *own_first, int *own_rows, int *halo_rows);
+int s2mv_band_prepare(s2mv_ctx *ctx, const uint8_t *d_img_sbs_frame, int num_cols_sbs, void *stream);
+int s2mv_band_pass(s2mv_ctx *ctx, int pass, void *stream);
+/* after_pass 1|2, view 0|1, side 0 (towards row 0) | 1, recv 0 (own rows the neighbour needs) | 1 (halo rows
+ * to fill); *bytes == 0 at the frame's edges */
+int s2mv_band_halo(s2mv_ctx *ctx, int after_pass, int view, int side, int recv, void **d_ptr, size_t *bytes);
+int s2mv_band_disp(s2mv_ctx *ctx, int view, float **d_plane);
+int s2mv_band_finish(s2mv_ctx *ctx, float *d_disp_l_band, float *d_disp_r_band, uint8_t *d_interlaced_band, void *stream);
+
 /* ---- asynchronous frame stream (the video loop, video_io.cpp:139-160) -----
  * The same frames through the same kernels as s2mv_process_sbs, with the host
  * <-> device copies (d_io.cu:43-44,153-154,205) taken off the critical path:

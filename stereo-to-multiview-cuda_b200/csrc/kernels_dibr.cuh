@@ -208,6 +208,9 @@ struct MuxArgs {
     int num_views, Hin, Win, Hout, Wout, variant;
     float y_interval, inv_y_interval;
     int rint_y;  // (int)roundf(y_interval)
+    // row band of a taller frame: local row 0 is frame row `row0`; the resampling and the interlace phase
+    // are those of the frame (Hframe_in x Hframe_out).  Whole image: 0, Hin, Hout.
+    int row0, Hframe_in, Hframe_out;
 };
 
 __device__ __forceinline__ uint8_t bilinear_u8(const uint8_t *__restrict__ data, int off, int x0, int x1, int y0,
@@ -229,9 +232,11 @@ k_mux(const MuxArgs a)
     int ty = blockIdx.y;
     if (tx >= a.Wout) return;
     float xs = __fmul_rn(__fdiv_rn((float)tx, (float)a.Wout), (float)a.Win);
-    float ys = __fmul_rn(__fdiv_rn((float)ty, (float)a.Hout), (float)a.Hin);
+    const int ty_local = ty;
+    ty += a.row0;  // frame row
+    float ys = __fmul_rn(__fdiv_rn((float)ty, (float)a.Hframe_out), (float)a.Hframe_in);
     xs = (float)fmin(fmax((double)xs, 0.0), (double)(float)(a.Win - 1));
-    ys = (float)fmin(fmax((double)ys, 0.0), (double)(float)(a.Hin - 1));
+    ys = (float)fmin(fmax((double)ys, 0.0), (double)(float)(a.Hframe_in - 1));
     const float xi = (float)a.num_views;
     float yv;
     if (a.variant == 2) {
@@ -247,10 +252,13 @@ k_mux(const MuxArgs a)
     int gv = rv + 1, bv = rv + 2;
     if (gv >= a.num_views) gv -= a.num_views;
     if (bv >= a.num_views) bv -= a.num_views;
-    const int x0 = (int)floorf(xs), y0 = (int)floorf(ys);
-    const int x1 = min(x0 + 1, a.Win - 1), y1 = min(y0 + 1, a.Hin - 1);
-    const float wx = __fsub_rn(xs, (float)x0), wy = __fsub_rn(ys, (float)y0);
-    uint8_t *o = a.out + ((size_t)ty * a.Wout + tx) * 3;
+    const int x0 = (int)floorf(xs), yf = (int)floorf(ys);
+    const int x1 = min(x0 + 1, a.Win - 1);
+    const float wx = __fsub_rn(xs, (float)x0), wy = __fsub_rn(ys, (float)yf);
+    // frame rows -> rows of this (sub-)image; a band's apron rows may fall outside it and are never kept
+    const int y0 = min(max(yf - a.row0, 0), a.Hin - 1);
+    const int y1 = min(max(min(yf + 1, a.Hframe_in - 1) - a.row0, 0), a.Hin - 1);
+    uint8_t *o = a.out + ((size_t)ty_local * a.Wout + tx) * 3;
     o[0] = bilinear_u8(a.views[bv], 0, x0, x1, y0, y1, wx, wy, a.Win);
     o[1] = bilinear_u8(a.views[gv], 1, x0, x1, y0, y1, wx, wy, a.Win);
     o[2] = bilinear_u8(a.views[rv], 2, x0, x1, y0, y1, wx, wy, a.Win);

@@ -59,6 +59,10 @@ struct LineArgs {
     int ln_first;  // first line of this launch (column strips of the vertical passes)
     int d_first;   // disparity of chunk 0 of this launch (chunk-sequential mode: one 128-disparity chunk per launch)
     int use_keys;  // WTA through 64-bit (cost, d) atomicMin keys: the disparity range spans several chunks/launches
+    // vertical passes of a row band: outputs are rows [v_begin, v_end), readable input rows [v_lo, v_hi)
+    // (whole image: 0, H, 0, H).  Row indices stay image rows; the volume pointers of a band are biased so
+    // that row v_lo is the first allocated one.
+    int v_begin, v_end, v_lo, v_hi;
 };
 
 // shared-memory bytes of one CTA
@@ -252,9 +256,10 @@ k_line(const LineArgs a)
     const int seg = blockIdx.x;
     const int vslot = blockIdx.z / a.nchunks, chunk = blockIdx.z % a.nchunks;
     const int W = a.W;
-    const int LEN = VERT ? a.H : W;
-    const int t0 = seg * a.S;
+    const int LEN = VERT ? a.v_end : W;            // end of the outputs along the line
+    const int t0 = (VERT ? a.v_begin : 0) + seg * a.S;
     const int Sact = min(a.S, LEN - t0);
+    const int IN_LO = VERT ? a.v_lo : 0, IN_HI = VERT ? a.v_hi : W;  // readable input positions
     const int halo = a.halo;
     const int P = a.S + 2 * halo, P4 = (P + 3) & ~3;
     const int d0 = a.d_first + chunk * Dc;
@@ -354,7 +359,7 @@ k_line(const LineArgs a)
         }
     } else {
         // tile <- volume, 16 B per cp.async; positions outside the line are never inside a window
-        const int p_lo = max(0, halo - t0), p_hi = min(P, LEN - t0 + halo);
+        const int p_lo = max(0, IN_LO + halo - t0), p_hi = min(P, IN_HI - t0 + halo);
         const long long step = (long long)TEAMS * (long long)pos_stride4 * 16;
         const char *srcp = reinterpret_cast<const char *>(a.in[vslot] + line_base4) +
                            (long long)(t0 - halo + team) * (long long)pos_stride4 * 16;

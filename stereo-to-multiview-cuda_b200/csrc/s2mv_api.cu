@@ -210,6 +210,9 @@ struct s2mv_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
     bool configured = false, timing = false, taps = false;
+    // row-band mode (s2mv_band.inl): this context is a sub-image of a taller frame
+    bool band = false;
+    int band_frame_rows = 0, band_ly0 = 0, band_o0 = 0, band_o1 = 0, band_vlo = 0, band_vhi = 0;
     int chunk_seq_mode = -1;  // -1 auto (when the full volumes do not fit), 0 never, 1 whenever D > 128
     s2mv_params prm;
     CostPlan plan;
@@ -401,7 +404,12 @@ static int build_luts(s2mv_ctx *c, float ad_coeff, float census_coeff, cudaStrea
     return S2MV_OK;
 }
 
-extern "C" int s2mv_configure(s2mv_ctx *c, const s2mv_params *p)
+struct BandSpec { int frame_rows, ly0, o0, o1, vlo, vhi; };
+static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *band);
+
+extern "C" int s2mv_configure(s2mv_ctx *c, const s2mv_params *p) { return configure_impl(c, p, nullptr); }
+
+static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *band)
 {
     if (!c || !p) return fail(S2MV_ERR_BAD_PARAM, "null argument");
     if (p->elem_sz != 3) return fail(S2MV_ERR_BAD_PARAM, "elem_sz must be 3 (BGR), got %d", p->elem_sz);
@@ -426,6 +434,11 @@ extern "C" int s2mv_configure(s2mv_ctx *c, const s2mv_params *p)
     TRY(set_kernel_attrs());
     c->prm = *p;
     c->plan = pl;
+    c->band = band != nullptr;
+    if (band) {
+        c->band_frame_rows = band->frame_rows; c->band_ly0 = band->ly0; c->band_o0 = band->o0; c->band_o1 = band->o1;
+        c->band_vlo = band->vlo; c->band_vhi = band->vhi;
+    }
     c->lut_ad_coeff = c->lut_cen_coeff = -1.f;
     const size_t n = (size_t)p->num_rows * p->num_cols;
     if (pl.nchunks > 1) {
@@ -435,14 +448,16 @@ extern "C" int s2mv_configure(s2mv_ctx *c, const s2mv_params *p)
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
         const double full = 2.0 * 2.0 * (double)n * pl.Dp * sizeof(float);
-        const bool want = c->chunk_seq_mode == 1 || (c->chunk_seq_mode < 0 && full > 0.85 * (double)free_b);
+        const bool want = !band && (c->chunk_seq_mode == 1 || (c->chunk_seq_mode < 0 && full > 0.85 * (double)free_b));
         if (want) {
             pl.chunk_seq = true;
             pl.LPtot = pl.LP;  // volume rows hold one chunk
             c->plan = pl;
         }
     }
-    const size_t vol_elems = 2 * n * (pl.chunk_seq ? 4 * pl.LP : pl.Dp);
+    // a row band keeps only its own rows plus usd halo rows either side of the volumes
+    const size_t vol_rows = band ? (size_t)(band->vhi - band->vlo) : (size_t)p->num_rows;
+    const size_t vol_elems = 2 * vol_rows * p->num_cols * (pl.chunk_seq ? 4 * pl.LP : pl.Dp);
     for (int v = 0; v < 2; ++v) {
         TRY(dev_alloc_t(c, &c->pix[v], n));
         TRY(dev_alloc_t(c, &c->cen[v], n));
@@ -598,40 +613,56 @@ static void fill_largs(const s2mv_ctx *c, LineArgs &a, int H, int W, int zd, flo
     a.halo = pl.usd; a.view_first = 0;
 }
 
-// The four aggregation passes over volume buffers A/B for `nviews` view slots (H, V, V, H;
-// d_ca_cross.cu:255-271).  from_ci: pass 1 builds its input in shared memory (A is only written).
-// to_wta: pass 4 reduces to disparities instead of storing (A is only read).
-static int launch_aggregate(s2mv_ctx *c, LineArgs a, float4 *A, float4 *B, size_t view_stride4, int nviews,
-                            bool from_ci, bool to_wta, cudaStream_t st)
+// Image rows a launch works on: outputs [own0, own1); the volume buffers hold rows [vlo, vhi) (a whole
+// image: 0, H, 0, H; a row band: its own rows plus usd halo rows either side).
+struct RowRange { int own0, own1, vlo, vhi; };
+
+// One of the four aggregation passes (H, V, V, H; d_ca_cross.cu:255-271) over volume buffers A/B for
+// `nviews` view slots.  pass 1: (CI ->) H : . -> A  [stage API: B -> A]; pass 2: V : A -> B; pass 3: V : B -> A;
+// pass 4: H : A -> B, or A -> disparities.  from_ci: pass 1 builds its input in shared memory (A is only
+// written).  to_wta: pass 4 reduces to disparities instead of storing (A is only read).
+static int launch_pass(s2mv_ctx *c, LineArgs a, int pass, float4 *A, float4 *B, size_t view_stride4, int nviews,
+                       bool from_ci, bool to_wta, const RowRange &rr, cudaStream_t st)
 {
     const CostPlan &pl = c->plan;
-    const int H = a.H, W = a.W;
-    const dim3 gh((W + pl.S_h - 1) / pl.S_h, H, nviews * a.nchunks);
-    const dim3 gv((H + pl.S_v - 1) / pl.S_v, W, nviews * a.nchunks);
-    // pass 1: (CI ->) H : . -> A      [stage API: B -> A is not needed; input planes are loaded into B]
-    a.S = pl.S_h;
-    for (int v = 0; v < nviews; ++v) { a.in[v] = B + v * view_stride4; a.out[v] = A + v * view_stride4; }
-    if (c->timing) CU(cudaEventRecord(c->kev[0], st));
-    if (from_ci) TRY(launch_line<LM_CI_H>(pl, gh, pl.smem_line_ci, st, a));
-    else TRY(launch_line<LM_H>(pl, gh, pl.smem_line_h, st, a));
-    if (c->timing) CU(cudaEventRecord(c->kev[1], st));
-    // passes 2, 3: V : A -> B, B -> A
-    a.S = pl.S_v;
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int v = 0; v < nviews; ++v) {
-            a.in[v] = (pass == 0 ? A : B) + v * view_stride4;
-            a.out[v] = (pass == 0 ? B : A) + v * view_stride4;
+    const int W = a.W, rows = rr.own1 - rr.own0;
+    if (rows <= 0) return S2MV_OK;
+    // bias the bases so that image row r lives at (r - vlo) of the allocation
+    const size_t bias = (size_t)rr.vlo * W * pl.LPtot;
+    const float4 *in_base = ((pass == 1 || pass == 3) ? B : A) - bias;
+    float4 *out_base = ((pass == 1 || pass == 3) ? A : B) - bias;
+    for (int v = 0; v < nviews; ++v) { a.in[v] = in_base + v * view_stride4; a.out[v] = out_base + v * view_stride4; }
+    a.v_begin = rr.own0; a.v_end = rr.own1; a.v_lo = rr.vlo; a.v_hi = rr.vhi;
+    if (pass == 1 || pass == 4) {
+        const dim3 gh((W + pl.S_h - 1) / pl.S_h, rows, nviews * a.nchunks);
+        a.S = pl.S_h;
+        a.ln_first = rr.own0;
+        if (pass == 1) {
+            if (from_ci) TRY(launch_line<LM_CI_H>(pl, gh, pl.smem_line_ci, st, a));
+            else TRY(launch_line<LM_H>(pl, gh, pl.smem_line_h, st, a));
+        } else {
+            if (to_wta) TRY(launch_line<LM_H_WTA>(pl, gh, pl.smem_line_h, st, a));
+            else TRY(launch_line<LM_H>(pl, gh, pl.smem_line_h, st, a));
         }
+    } else {
+        const dim3 gv((rows + pl.S_v - 1) / pl.S_v, W, nviews * a.nchunks);
+        a.S = pl.S_v;
+        a.ln_first = 0;
         TRY(launch_line<LM_V>(pl, gv, pl.smem_line_v, st, a));
-        if (c->timing) CU(cudaEventRecord(c->kev[2 + pass], st));
     }
-    // pass 4: H : A -> B, or A -> disparities
-    a.S = pl.S_h;
-    for (int v = 0; v < nviews; ++v) { a.in[v] = A + v * view_stride4; a.out[v] = B + v * view_stride4; }
-    if (to_wta) TRY(launch_line<LM_H_WTA>(pl, gh, pl.smem_line_h, st, a));
-    else TRY(launch_line<LM_H>(pl, gh, pl.smem_line_h, st, a));
-    if (c->timing) CU(cudaEventRecord(c->kev[4], st));
-    c->launches += 4;
+    c->launches += 1;
+    return S2MV_OK;
+}
+
+static int launch_aggregate(s2mv_ctx *c, const LineArgs &a, float4 *A, float4 *B, size_t view_stride4, int nviews,
+                            bool from_ci, bool to_wta, cudaStream_t st)
+{
+    const RowRange rr = {0, a.H, 0, a.H};
+    if (c->timing) CU(cudaEventRecord(c->kev[0], st));
+    for (int pass = 1; pass <= 4; ++pass) {
+        TRY(launch_pass(c, a, pass, A, B, view_stride4, nviews, from_ci, to_wta, rr, st));
+        if (c->timing) CU(cudaEventRecord(c->kev[pass], st));
+    }
     return S2MV_OK;
 }
 
@@ -786,12 +817,14 @@ static int launch_gauss(s2mv_ctx *c, const float *in, float *out, const float *k
 }
 
 static int launch_mux(s2mv_ctx *c, const uint8_t *const *views, uint8_t *out, int V, float angle, int Hin, int Win,
-                      int Hout, int Wout, int elem_sz, int variant, cudaStream_t st)
+                      int Hout, int Wout, int elem_sz, int variant, cudaStream_t st, int row0 = 0, int Hframe_in = 0,
+                      int Hframe_out = 0)
 {
     MuxArgs m;
     memset(&m, 0, sizeof(m));
     for (int v = 0; v < V; ++v) m.views[v] = views[v];
     m.out = out; m.num_views = V; m.Hin = Hin; m.Win = Win; m.Hout = Hout; m.Wout = Wout;
+    m.row0 = row0; m.Hframe_in = Hframe_in ? Hframe_in : Hin; m.Hframe_out = Hframe_out ? Hframe_out : Hout;
     // d_mux_multiview.cu:146 (PI is the float literal 3.1415926535f)
     float yi = (float)((double)(float)V / tan((double)(angle * 3.1415926535f) / 180.0) / (double)(float)elem_sz);
     m.y_interval = yi;
@@ -807,33 +840,13 @@ static int launch_mux(s2mv_ctx *c, const uint8_t *const *views, uint8_t *out, in
 }
 
 // --------------------------------------------------------- frame pipeline
-static int run_frame(s2mv_ctx *c, const uint8_t *d_sbs, int num_cols_sbs, float *d_disp_l, float *d_disp_r,
-                     uint8_t *d_interlaced, bool costvol_only, cudaStream_t st)
+// Refinement (cross-check, region voting, bilateral; d_io.cu:139-151) and DIBR + interlace
+// (d_io.cu:160-236) from the WTA disparities in c->disp[].  Records timing events 3 and 4.
+static int run_refine_dibr(s2mv_ctx *c, float *d_disp_l, float *d_disp_r, uint8_t *d_interlaced, cudaStream_t st)
 {
     const s2mv_params &p = c->prm;
     const int H = p.num_rows, W = p.num_cols, V = p.num_views;
     const size_t n = (size_t)H * W;
-    if (num_cols_sbs < 2 * W) return fail(S2MV_ERR_BAD_PARAM, "num_cols_sbs (%d) < 2*num_cols (%d)", num_cols_sbs, 2 * W);
-    c->launches = 0;
-    if (c->timing) CU(cudaEventRecord(c->ev[0], st));
-    // views[0] = right image, views[V-1] = left image (d_io.cu:181-182)
-    uint8_t *view0 = c->views, *viewN = c->views + (size_t)(V - 1) * n * 3;
-    TRY(launch_prepare(c, d_sbs, d_sbs + (size_t)W * 3, (size_t)num_cols_sbs * 3, costvol_only ? nullptr : viewN,
-                       costvol_only ? nullptr : view0, st));
-    TRY(build_luts(c, p.ad_coeff, p.census_coeff, st));
-    if (c->timing) CU(cudaEventRecord(c->ev[1], st));
-
-    float *wl = costvol_only && d_disp_l ? d_disp_l : c->disp[0];
-    float *wr = costvol_only && d_disp_r ? d_disp_r : c->disp[1];
-    TRY(launch_costvol(c, wl, wr, st));
-    if (c->timing) CU(cudaEventRecord(c->ev[2], st));
-    if (costvol_only) {
-        if (c->timing) {
-            CU(cudaEventRecord(c->ev[3], st));
-            CU(cudaEventRecord(c->ev[4], st));
-        }
-        return S2MV_OK;
-    }
     if (c->taps)
         for (int v = 0; v < 2; ++v)
             CU(cudaMemcpyAsync(c->tap_wta[v], c->disp[v], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -891,9 +904,41 @@ static int run_frame(s2mv_ctx *c, const uint8_t *d_sbs, int num_cols_sbs, float 
     const uint8_t *vp[16];
     for (int v = 0; v < V; ++v) vp[v] = c->views + (size_t)v * n * 3;
     TRY(launch_mux(c, vp, d_interlaced ? d_interlaced : c->interlaced, V, (float)p.angle, H, W, p.num_rows_out,
-                   p.num_cols_out, p.elem_sz, 2, st));
+                   p.num_cols_out, p.elem_sz, 2, st, c->band ? c->band_ly0 : 0, c->band ? c->band_frame_rows : 0,
+                   c->band ? c->band_frame_rows : 0));
     if (c->timing) CU(cudaEventRecord(c->ev[4], st));
     return S2MV_OK;
+}
+
+static int run_frame(s2mv_ctx *c, const uint8_t *d_sbs, int num_cols_sbs, float *d_disp_l, float *d_disp_r,
+                     uint8_t *d_interlaced, bool costvol_only, cudaStream_t st)
+{
+    const s2mv_params &p = c->prm;
+    const int H = p.num_rows, W = p.num_cols, V = p.num_views;
+    const size_t n = (size_t)H * W;
+    if (num_cols_sbs < 2 * W) return fail(S2MV_ERR_BAD_PARAM, "num_cols_sbs (%d) < 2*num_cols (%d)", num_cols_sbs, 2 * W);
+    if (c->band) return fail(S2MV_ERR_BAD_PARAM, "this context is a row band: use the s2mv_band_* sequence");
+    c->launches = 0;
+    if (c->timing) CU(cudaEventRecord(c->ev[0], st));
+    // views[0] = right image, views[V-1] = left image (d_io.cu:181-182)
+    uint8_t *view0 = c->views, *viewN = c->views + (size_t)(V - 1) * n * 3;
+    TRY(launch_prepare(c, d_sbs, d_sbs + (size_t)W * 3, (size_t)num_cols_sbs * 3, costvol_only ? nullptr : viewN,
+                       costvol_only ? nullptr : view0, st));
+    TRY(build_luts(c, p.ad_coeff, p.census_coeff, st));
+    if (c->timing) CU(cudaEventRecord(c->ev[1], st));
+
+    float *wl = costvol_only && d_disp_l ? d_disp_l : c->disp[0];
+    float *wr = costvol_only && d_disp_r ? d_disp_r : c->disp[1];
+    TRY(launch_costvol(c, wl, wr, st));
+    if (c->timing) CU(cudaEventRecord(c->ev[2], st));
+    if (costvol_only) {
+        if (c->timing) {
+            CU(cudaEventRecord(c->ev[3], st));
+            CU(cudaEventRecord(c->ev[4], st));
+        }
+        return S2MV_OK;
+    }
+    return run_refine_dibr(c, d_disp_l, d_disp_r, d_interlaced, st);
 }
 
 extern "C" int s2mv_process_sbs_device(s2mv_ctx *c, const uint8_t *d_img_sbs, int num_cols_sbs, float *d_disp_l,
@@ -1047,3 +1092,4 @@ extern "C" int s2mv_read_taps(s2mv_ctx *c, float *wta_l, float *wta_r, uint8_t *
 
 #include "s2mv_stages.inl"
 #include "s2mv_stream.inl"
+#include "s2mv_band.inl"

@@ -80,3 +80,79 @@ def test_upscale_follows_reference_formula(s2mv):
     assert up.shape == (8, 12, 3)
     assert np.array_equal(up[::2, ::2], img)                             # even samples land on source pixels
     assert up[1, 1, 0] == int((img[0, 0, 0] + img[0, 1, 0] + img[1, 0, 0] + img[1, 1, 0]) / 4.0)
+
+
+def test_row_band_partition_and_schedules(s2mv):
+    from s2mv_b200_pkg.rowband import gather_rows, halo_schedule, row_bands
+    for H in (64, 1080, 2160, 4321):
+        for n in (1, 2, 3, 8):
+            bands = row_bands(H, n, min_rows=4)
+            assert bands[0][0] == 0 and bands[-1][1] == H
+            assert all(a[1] == b[0] for a, b in zip(bands, bands[1:]))
+            sizes = [y1 - y0 for y0, y1 in bands]
+            assert max(sizes) - min(sizes) <= 1
+            # every transfer has its mirror image on the peer: what b sends towards side s, the peer receives
+            # on the opposite side of its own band
+            for b in range(n):
+                for peer, send_side, recv_side in halo_schedule(b, n):
+                    assert abs(peer - b) == 1 and send_side == recv_side == (0 if peer < b else 1)
+                    assert (b, 1 - send_side, 1 - recv_side) in halo_schedule(peer, n)
+            # a sub-image's rows are covered exactly once by the bands' own rows
+            for b, (y0, y1) in enumerate(bands):
+                lo, hi = max(0, y0 - 128), min(H, y1 + 128)
+                got = gather_rows(bands, lo, hi - lo)
+                assert sum(e - a for _, a, e in got) == hi - lo
+                assert [a for _, a, _ in got] == sorted(a for _, a, _ in got)
+    import pytest
+    with pytest.raises(ValueError):
+        row_bands(30, 2, min_rows=17)
+
+
+def test_two_rank_gloo_halo_exchange_and_row_gather(s2mv, tmp_path):
+    """The distributed transport of the row-band mode on CPU tensors over gloo (world_size 2): after the
+    exchange each rank's halo rows hold the neighbour's edge rows, and the row all-gather rebuilds the frame
+    from uneven bands."""
+    script = tmp_path / "worker.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys
+        sys.path.insert(0, {ROOT!r})
+        import torch, torch.distributed as dist
+        import s2mv_b200
+        from s2mv_b200_pkg import sharding, rowband
+        rank, world, _ = sharding.dist_env()
+        assert sharding.init_process_group("gloo")
+        H, W, usd = 41, 6, 3
+        bands = rowband.row_bands(H, world, min_rows=usd)
+        y0, y1 = bands[rank]
+        frame = torch.arange(H * W, dtype=torch.float32).reshape(H, W)
+        # a band's volume rows: own rows + usd halo rows either side (clipped), two views
+        vlo, vhi = max(0, y0 - usd), min(H, y1 + usd)
+        vol = [torch.full((vhi - vlo, W), -1.0) for _ in range(2)]
+        for v in range(2):
+            vol[v][y0 - vlo:y1 - vlo] = frame[y0:y1] + 1000 * v
+        def send_recv(side, recv):
+            if side == 0:
+                r0 = (y0 - usd if recv else y0)
+                if y0 == 0: return None
+            else:
+                r0 = (y1 if recv else y1 - usd)
+                if y1 == H: return None
+            return [vol[v][r0 - vlo:r0 - vlo + usd] for v in range(2)]
+        rowband.exchange_halos_dist(send_recv, rank, world, dist)
+        for v in range(2):
+            assert torch.equal(vol[v], frame[vlo:vhi] + 1000 * v), (rank, v)
+        full = rowband.allgather_rows_dist(frame[y0:y1].clone(), bands, dist, torch)
+        assert torch.equal(full, frame)
+        print("RESULT ok", rank)
+    """))
+    port = _free_port()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=180) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e
+        assert "RESULT ok" in o
