@@ -57,6 +57,10 @@ struct IrvArgs {
     int *next_count[2];  // length of next
     int H, W, nbins, zd, usd, thresh_s;
     float thresh_h;
+    // dense path (k_irv_hseg + k_irv_vote_dense): per-pixel histograms of the horizontal arm span
+    uint8_t *hseg[2];    // [pixel][nbp] counts, nbp = nbins rounded up to a multiple of 128; null: sparse path only
+    int nbp;
+    int dense_min;       // list length from which an iteration takes the dense path
 };
 constexpr int kNoVote = -0x7fffffff;
 
@@ -119,6 +123,7 @@ k_irv_vote(const IrvArgs a)
     int *hist = hist_all + warp * a.nbins;
     const int count = *a.count[v];
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.next_count[v] = 0;  // consumed by k_irv_apply, which runs after
+    if (a.hseg[v] && count >= a.dense_min) return;                  // this iteration is k_irv_vote_dense's
     const float *__restrict__ disp = a.disp[v];
     const uint8_t *__restrict__ outl = a.outliers[v];
     const uint32_t *__restrict__ arms = a.arms[v];
@@ -166,6 +171,110 @@ k_irv_vote(const IrvArgs a)
             int max_d = (best > 0) ? (bestb - a.zd) : (int)disp[pix];
             // dr_irv_kernel_3: ratio test on the histogram INDEX (Q16)
             bool ok = cnt > a.thresh_s && __fdiv_rn((float)(max_d + a.zd), (float)cnt) > a.thresh_h;
+            a.vote[v][e] = ok ? max_d : kNoVote;
+        }
+    }
+}
+
+// ---- dense path ------------------------------------------------------------
+// With many outliers (occlusion-heavy frames: half the pixels of the synthetic streams) the per-outlier
+// gather above re-reads every support row once per outlier of its column.  The vote histogram of outlier p
+// is the sum, over the pixels q of p's vertical arm, of the histogram of q's horizontal span -- and that
+// inner histogram depends on q alone.  k_irv_hseg builds it once per pixel (8-bit counts: a span holds at
+// most 2*usd+1 <= 129 pixels), k_irv_vote_dense adds <= 2*usd+1 of them per outlier with packed 16-bit
+// adds: one coalesced 128-byte load per support row instead of a row of scattered loads and shared-memory
+// atomics.  Same histogram, same count, same first-maximum rule as k_irv_vote.
+constexpr int kHsegThreads = 128;
+
+__global__ void __launch_bounds__(kHsegThreads)
+k_irv_hseg(const IrvArgs a)
+{
+    extern __shared__ __align__(16) uint8_t hs[];  // [kHsegThreads][nbp + 4]: the pad staggers the banks
+    const int v = blockIdx.y;
+    if (*a.count[v] < a.dense_min) return;
+    const int W = a.W, nbp = a.nbp, pitch = nbp + 4;
+    const int tiles_x = (W + kHsegThreads - 1) / kHsegThreads, ntiles = tiles_x * a.H;
+    const float *__restrict__ disp = a.disp[v];
+    const uint8_t *__restrict__ outl = a.outliers[v];
+    const uint32_t *__restrict__ arms = a.arms[v];
+    uint8_t *__restrict__ hseg = a.hseg[v];
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    uint32_t *hw = reinterpret_cast<uint32_t *>(hs);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int gy = tile / tiles_x, bx = (tile - gy * tiles_x) * kHsegThreads;
+        for (int i = t; i < kHsegThreads * pitch / 4; i += kHsegThreads) hw[i] = 0u;
+        __syncthreads();
+        const int gx = bx + t;
+        if (gx < W) {
+            const size_t row = (size_t)gy * W;
+            const uint32_t ar = arms[row + gx];
+            const int cl = arm_left(ar), span = cl + arm_right(ar) + 1;  // inclusive [-L, R]
+            const float *__restrict__ dp = disp + row + (gx - cl);
+            const uint8_t *__restrict__ op = outl + row + (gx - cl);
+            uint8_t *mine = hs + t * pitch;
+            for (int k = 0; k < span; ++k)
+                if (op[k] == 0) mine[clampi((int)dp[k] + a.zd, 0, a.nbins - 1)] += 1;
+        }
+        __syncthreads();
+        const int npix = min(kHsegThreads, W - bx);
+        uint32_t *__restrict__ dst = reinterpret_cast<uint32_t *>(hseg + ((size_t)gy * W + bx) * nbp);
+        for (int i = warp; i < npix; i += kHsegThreads / 32)
+            for (int w = lane; w < nbp / 4; w += 32) dst[(size_t)i * (nbp / 4) + w] = hw[i * (pitch / 4) + w];
+        __syncthreads();
+    }
+}
+
+template <int NW>  // 128-bin words per lane: nbp = 128 * NW
+__global__ void __launch_bounds__(kIrvWarps * 32)
+k_irv_vote_dense(const IrvArgs a)
+{
+    const int v = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int count = *a.count[v];
+    if (count < a.dense_min) return;
+    const float *__restrict__ disp = a.disp[v];
+    const uint32_t *__restrict__ arms = a.arms[v];
+    const uint32_t *__restrict__ hseg = reinterpret_cast<const uint32_t *>(a.hseg[v]);
+    const int W = a.W;
+    constexpr int WPP = 32 * NW;  // 32-bit words per pixel
+    for (int e = blockIdx.x * kIrvWarps + warp; e < count; e += gridDim.x * kIrvWarps) {
+        const int pix = a.list[v][e];
+        const int gy = pix / W, gx = pix - gy * W;
+        const uint32_t ac = arms[pix];
+        const int cu = min(arm_up(ac), a.usd), nrows = cu + arm_down(ac) + 1;  // rows [-cu, +cd] inclusive
+        uint32_t lo[NW], hi[NW];  // 16-bit fields: bins (0, 2) and (1, 3) of each packed word
+#pragma unroll
+        for (int w = 0; w < NW; ++w) lo[w] = hi[w] = 0u;
+        const uint32_t *__restrict__ p = hseg + ((size_t)(gy - cu) * W + gx) * WPP + lane;
+#pragma unroll 4
+        for (int r = 0; r < nrows; ++r, p += (size_t)W * WPP) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const uint32_t x = __ldg(p + 32 * w);
+                lo[w] += x & 0x00ff00ffu;
+                hi[w] += (x >> 8) & 0x00ff00ffu;
+            }
+        }
+        // total count; first bin holding the maximum count: maximise (count, -bin)
+        uint32_t cnt = 0, key = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t c[4] = {lo[w] & 0xffffu, hi[w] & 0xffffu, lo[w] >> 16, hi[w] >> 16};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                cnt += c[j];
+                const uint32_t bin = (uint32_t)(128 * w + 4 * lane + j);
+                const uint32_t k = c[j] ? ((c[j] << 10) | (1023u - bin)) : 0u;
+                key = max(key, k);
+            }
+        }
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        key = __reduce_max_sync(0xffffffffu, key);
+        if (lane == 0) {
+            const int best = (int)(key >> 10), bestb = 1023 - (int)(key & 1023u);
+            int max_d = (best > 0) ? (bestb - a.zd) : (int)disp[pix];
+            // dr_irv_kernel_3: ratio test on the histogram INDEX (Q16)
+            bool ok = (int)cnt > a.thresh_s && __fdiv_rn((float)(max_d + a.zd), (float)(int)cnt) > a.thresh_h;
             a.vote[v][e] = ok ? max_d : kNoVote;
         }
     }

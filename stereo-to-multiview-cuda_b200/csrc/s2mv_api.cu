@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -231,6 +232,8 @@ struct s2mv_ctx {
     float *disp[2] = {}, *dispF[2] = {};  // WTA/IRV disparities; bilateral output
     uint8_t *outl[2] = {}, *disoccl[2] = {};
     int *irv_list[2] = {}, *irv_list2[2] = {}, *irv_vote[2] = {}, *irv_count = nullptr;
+    uint8_t *irv_hseg[2] = {};  // dense region-voting histograms, [pixel][nbp]; null when not allocated
+    int irv_nbp = 0;
     float *bil_spatial = nullptr, *bil_colour = nullptr, *gauss_kernel = nullptr;
     std::vector<float> h_gauss_kernel;  // host copy of gauss_kernel (for its fp32 sum)
     uint8_t *occl[2] = {}, *occlB[2] = {};
@@ -371,6 +374,7 @@ static int set_kernel_attrs()
     TRY(set_smem(k_gauss_dilate4<10>, 64 * 1024));
     TRY(set_smem(k_gauss_dilate, 160 * 1024));
     TRY(set_smem(k_irv_vote, 64 * 1024));
+    TRY(set_smem(k_irv_hseg, 100 * 1024));
     TRY(set_smem(k_arms_tile, 160 * 1024));
     return S2MV_OK;
 }
@@ -478,6 +482,18 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
         TRY(dev_alloc_t(c, &c->tap_outl[v], n));
         if (pl.nchunks > 1) TRY(dev_alloc_t(c, &c->wta_key[v], n));
         TRY(dev_alloc_t(c, &c->vol[v], vol_elems));
+    }
+    {   // dense region voting: one byte per (pixel, histogram bin); skipped when it would crowd the device
+        const int nbins = p->num_disp > 65 ? p->num_disp : 65, nbp = ((nbins + 127) / 128) * 128;
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        c->irv_hseg[0] = c->irv_hseg[1] = nullptr;
+        c->irv_nbp = 0;
+        if (nbp <= 512 && 2.0 * (double)n * nbp < 0.25 * (double)free_b) {
+            TRY(dev_alloc_t(c, &c->irv_hseg[0], n * nbp));
+            TRY(dev_alloc_t(c, &c->irv_hseg[1], n * nbp));
+            c->irv_nbp = nbp;
+        }
     }
     TRY(dev_alloc_t(c, &c->irv_count, 4));
     TRY(dev_alloc_t(c, &c->tmask, n));
@@ -738,7 +754,26 @@ static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2],
     k_irv_compact<<<dim3((unsigned)((n + 4095) / 4096), nviews), 256, 0, st>>>(a);
     KCHECK();
     c->launches += 1;
+    // lists longer than 1/64 of the image take the dense path (decided on the device, per iteration and view)
+    const bool dense_ok = c->irv_hseg[0] && c->irv_nbp >= a.nbins && (size_t)H * W == (size_t)c->prm.num_rows * c->prm.num_cols;
+    a.nbp = c->irv_nbp;
+    a.dense_min = (int)(n / 64) + 1;
+    if (const char *e = getenv("S2MV_IRV_DENSE_MIN")) a.dense_min = atoi(e);  // test hook: 0 = always dense, huge = never
+    for (int v = 0; v < nviews; ++v) a.hseg[v] = dense_ok ? c->irv_hseg[v] : nullptr;
     for (int it = 0; it < iterations; ++it) {
+        if (dense_ok) {
+            k_irv_hseg<<<dim3(c->sm_count * 8, nviews), kHsegThreads, (size_t)kHsegThreads * (a.nbp + 4), st>>>(a);
+            KCHECK();
+            const dim3 gd(c->sm_count * 8, nviews);
+            switch (a.nbp / 128) {
+                case 1: k_irv_vote_dense<1><<<gd, kIrvWarps * 32, 0, st>>>(a); break;
+                case 2: k_irv_vote_dense<2><<<gd, kIrvWarps * 32, 0, st>>>(a); break;
+                case 3: k_irv_vote_dense<3><<<gd, kIrvWarps * 32, 0, st>>>(a); break;
+                default: k_irv_vote_dense<4><<<gd, kIrvWarps * 32, 0, st>>>(a); break;
+            }
+            KCHECK();
+            c->launches += 2;
+        }
         k_irv_vote<<<dim3(c->sm_count * 4, nviews), kIrvWarps * 32, hist_bytes, st>>>(a);
         KCHECK();
         k_irv_apply<<<dim3(c->sm_count, nviews), 256, 0, st>>>(a);
