@@ -162,6 +162,10 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    # the single JSON line must be the only thing on stdout: NCCL prints its version banner there at
+    # NCCL_DEBUG=VERSION
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import s2mv_b200
     from s2mv_b200_pkg import sharding
