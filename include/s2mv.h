@@ -101,6 +101,11 @@ int s2mv_process_sbs_device(s2mv_ctx *ctx, const uint8_t *d_img_sbs, int num_col
 int s2mv_costvol_device(s2mv_ctx *ctx, const uint8_t *d_img_sbs, int num_cols_sbs,
                         float *d_disp_l, float *d_disp_r, void *stream);
 
+/* Frame path option (default off: adcensus_stm never runs it): scanline optimisation of both views between
+ * cross aggregation and winner-takes-all, with image_io.cpp:311-313's T = 15, H1 = 1, H2 = 3 or the
+ * caller's.  Needs num_disp <= 128 and a whole-frame context. */
+int s2mv_enable_so(s2mv_ctx *ctx, int on, float T, float H1, float H2);
+
 int s2mv_synchronize(s2mv_ctx *ctx);
 
 /* ---- row-band mode: ONE frame over several contexts / GPUs ----------------
@@ -215,6 +220,14 @@ int s2mv_ca_cross(s2mv_ctx *ctx, const uint8_t *img, uint8_t **cross, float **co
 /* d_dc_wta.cu:61-122 */
 int s2mv_dc_wta(s2mv_ctx *ctx, float **cost, float *disp, int num_disp, int zero_disp,
                 int num_rows, int num_cols);
+/* Scanline optimisation + WTA of ONE view's aggregated cost: the stage the reference declares as dc_hslo
+ * (d_dc_hslo.cu:97-101) but never finished or called (image_io.cpp:307-316) -- PARITY UNPINNED, there is no
+ * reference output; the specification is oracle/s2mv_oracle.c:orc_so (Mei et al. 2011, four directions, the
+ * stub's constants, colour measure and penalty tiers).  view 0: img_own = left image, 1: img_own = right.
+ * disp and cost_out (num_disp planes receiving the optimised cost) may each be NULL.  num_disp <= 128. */
+int s2mv_dc_so(s2mv_ctx *ctx, float **cost, float *disp, float **cost_out, const uint8_t *img_own,
+               const uint8_t *img_other, int view, float T, float H1, float H2,
+               int num_disp, int zero_disp, int num_rows, int num_cols, int elem_sz);
 /* d_dr_dcc.cu:130-205 */
 int s2mv_dr_dcc(s2mv_ctx *ctx, uint8_t *outliers_l, uint8_t *outliers_r,
                 const float *disp_l, const float *disp_r, int num_rows, int num_cols);

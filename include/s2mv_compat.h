@@ -23,6 +23,10 @@ void ca_cross(unsigned char *img, unsigned char **cross, float **cost, float **a
               int usd, int lsd, int num_disp, int num_rows, int num_cols, int elem_sz);
 /* d_dc_wta.h       _Z6dc_wtaPPfS_iiii */
 void dc_wta(float **cost, float *disp, int num_disp, int zero_disp, int num_rows, int num_cols);
+/* d_dc_hslo.h:19-23  _Z7dc_hsloPPfS_PhS1_fffiiiii — a stub in the reference (it allocates, computes penalty maps
+ * and returns); here the scanline optimisation it was meant to be, for the left view (s2mv.h: s2mv_dc_so) */
+void dc_hslo(float **cost, float *disp, unsigned char *img_l, unsigned char *img_r, float T, float H1, float H2,
+             int num_disp, int zero_disp, int num_rows, int num_cols, int elem_sz);
 /* d_dr_dcc.h       _Z6dr_dccPhS_PfS0_ii */
 void dr_dcc(unsigned char *outliers_l, unsigned char *outliers_r, float *disp_l, float *disp_r, int num_rows,
             int num_cols);

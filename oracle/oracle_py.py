@@ -146,6 +146,16 @@ def wta(cost, zd):
     return disp
 
 
+def so(cost, img_own, img_other, view, T, H1, H2, zd, want_cost=False):
+    """Scanline optimisation + WTA (PARITY UNPINNED: specification, not a restatement; see s2mv_oracle.c)."""
+    D, H, W = cost.shape
+    disp = np.zeros((H, W), np.float32)
+    out = np.zeros_like(cost) if want_cost else None
+    lib().orc_so(_p(np.ascontiguousarray(cost, np.float32)), _p(out), _p(disp), _p(np.ascontiguousarray(img_own)),
+                 _p(np.ascontiguousarray(img_other)), int(view), _f(T), _f(H1), _f(H2), D, zd, H, W, 3)
+    return (disp, out) if want_cost else disp
+
+
 def dcc(disp_l, disp_r):
     H, W = disp_l.shape
     ol = np.zeros((H, W), np.uint8)

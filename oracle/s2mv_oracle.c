@@ -357,6 +357,94 @@ void orc_wta(const float *cost, float *disp, int num_disp, int zero_disp, int nu
     }
 }
 
+/* ------------------------------------------------- scanline optimisation */
+/* PARITY UNPINNED: the reference's d_dc_hslo.cu is an unfinished stub (its kernels compute penalty maps
+ * and nothing else, d_dc_hslo.cu:9-95; the only call site is commented out, image_io.cpp:307-316), so
+ * there is no reference output to match.  This function is the SPECIFICATION of the stage as built
+ * here: the four-direction scanline optimisation of Mei et al. 2011 ("On Building an Accurate Stereo
+ * Matching System on Graphics Hardware", named in the reference's README:4) with everything the stub does
+ * define taken from it: the call shape (d_dc_hslo.cu:97-101), the constants T = 15, H1 = 1.0, H2 = 3.0
+ * (image_io.cpp:311-313), the colour measure (mean of B, G, R; d_dc_hslo.cu:55-70), the three penalty tiers
+ * H, H/4, H/10 and their strict comparisons (d_dc_hslo.cu:73-93, 124-127).
+ *
+ *   C_r(p, d) = C(p, d) + min( C_r(p-r, d), C_r(p-r, d-1) + P1, C_r(p-r, d+1) + P1, m + P2 ) - m,
+ *               m = min_k C_r(p-r, k);     C_r = C on the first pixel of a scanline
+ *   D1 = |g_own(p) - g_own(p-r)|,  D2 = |g_other(q) - g_other(q-r)|,  g = (B + G + R) / 3,
+ *               q = p shifted by +(d - zd) columns for the left view, -(d - zd) for the right (clamped)
+ *   (P1, P2) = (H1, H2) if D1 < T and D2 < T;  (H1/4, H2/4) if exactly one of them is < T and the other > T;
+ *              (H1/10, H2/10) otherwise
+ *   C2 = (((C_lr + C_rl) + C_tb) + C_bt) * 0.25,  r = (+1,0), (-1,0), (0,+1), (0,-1) in that order
+ * followed by winner-takes-all (first minimum, as orc_wta).  fp32 throughout, one rounding per operation
+ * in exactly the order written.  cost: [d][y][x]; `cost_out` (may be NULL) receives C2. */
+static inline float so_gray(const uint8_t *img, int x, int y, int num_cols, int elem_sz)
+{
+    const uint8_t *p = img + ((size_t)y * num_cols + x) * elem_sz;
+    return (float)((int)p[0] + (int)p[1] + (int)p[2]) / 3.0f;
+}
+
+static void so_direction(const float *cost, float *acc, int first, const uint8_t *img_own, const uint8_t *img_other,
+                         int view, int dx, int dy, float T, float H1, float H2, int num_disp, int zero_disp,
+                         int num_rows, int num_cols, int elem_sz)
+{
+    const size_t plane = (size_t)num_rows * num_cols;
+    const int nlines = dx ? num_rows : num_cols, len = dx ? num_cols : num_rows;
+    const float P1t[3] = {H1, H1 / 4.0f, H1 / 10.0f}, P2t[3] = {H2, H2 / 4.0f, H2 / 10.0f};
+#pragma omp parallel for schedule(static)
+    for (int ln = 0; ln < nlines; ++ln) {
+        float *prev = (float *)malloc(sizeof(float) * num_disp), *cur = (float *)malloc(sizeof(float) * num_disp);
+        for (int t = 0; t < len; ++t) {
+            const int k = (dx > 0 || dy > 0) ? t : len - 1 - t;
+            const int x = dx ? k : ln, y = dx ? ln : k;
+            const size_t i = (size_t)y * num_cols + x;
+            if (t == 0) {
+                for (int d = 0; d < num_disp; ++d) cur[d] = cost[d * plane + i];
+            } else {
+                const int px = x - dx, py = y - dy;
+                float m = prev[0];
+                for (int d = 1; d < num_disp; ++d) m = prev[d] < m ? prev[d] : m;
+                const float D1 = fabsf(so_gray(img_own, x, y, num_cols, elem_sz) - so_gray(img_own, px, py, num_cols, elem_sz));
+                for (int d = 0; d < num_disp; ++d) {
+                    const int sh = view == 0 ? (d - zero_disp) : -(d - zero_disp);
+                    const int qx = x + sh < 0 ? 0 : (x + sh > num_cols - 1 ? num_cols - 1 : x + sh);
+                    const int qpx = px + sh < 0 ? 0 : (px + sh > num_cols - 1 ? num_cols - 1 : px + sh);
+                    const float D2 = fabsf(so_gray(img_other, qx, y, num_cols, elem_sz) - so_gray(img_other, qpx, py, num_cols, elem_sz));
+                    int tier;
+                    if (D1 < T && D2 < T) tier = 0;
+                    else if ((D1 < T && D2 > T) || (D1 > T && D2 < T)) tier = 1;
+                    else tier = 2;
+                    const float P1 = P1t[tier], P2 = P2t[tier];
+                    float best = prev[d];
+                    if (d > 0) { const float v = prev[d - 1] + P1; best = v < best ? v : best; }
+                    if (d < num_disp - 1) { const float v = prev[d + 1] + P1; best = v < best ? v : best; }
+                    { const float v = m + P2; best = v < best ? v : best; }
+                    cur[d] = (cost[d * plane + i] + best) - m;
+                }
+            }
+            for (int d = 0; d < num_disp; ++d) {
+                if (first) acc[d * plane + i] = cur[d];
+                else acc[d * plane + i] = acc[d * plane + i] + cur[d];
+            }
+            float *tmp = prev; prev = cur; cur = tmp;
+        }
+        free(prev); free(cur);
+    }
+}
+
+void orc_so(const float *cost, float *cost_out, float *disp, const uint8_t *img_own, const uint8_t *img_other,
+            int view, float T, float H1, float H2, int num_disp, int zero_disp, int num_rows, int num_cols, int elem_sz)
+{
+    const size_t n = (size_t)num_rows * num_cols * num_disp;
+    float *acc = (float *)malloc(sizeof(float) * n);
+    so_direction(cost, acc, 1, img_own, img_other, view, +1, 0, T, H1, H2, num_disp, zero_disp, num_rows, num_cols, elem_sz);
+    so_direction(cost, acc, 0, img_own, img_other, view, -1, 0, T, H1, H2, num_disp, zero_disp, num_rows, num_cols, elem_sz);
+    so_direction(cost, acc, 0, img_own, img_other, view, 0, +1, T, H1, H2, num_disp, zero_disp, num_rows, num_cols, elem_sz);
+    so_direction(cost, acc, 0, img_own, img_other, view, 0, -1, T, H1, H2, num_disp, zero_disp, num_rows, num_cols, elem_sz);
+    for (size_t i = 0; i < n; ++i) acc[i] = acc[i] * 0.25f;
+    if (disp) orc_wta(acc, disp, num_disp, zero_disp, num_rows, num_cols);
+    if (cost_out) memcpy(cost_out, acc, sizeof(float) * n);
+    free(acc);
+}
+
 /* ------------------------------------------------------------------ DCC */
 void orc_dcc(uint8_t *outliers_l, uint8_t *outliers_r, const float *disp_l, const float *disp_r,
              int num_rows, int num_cols)

@@ -66,6 +66,10 @@ void orc_ca_pass(const float *in, float *out, const uint8_t *arms, int dir,
                  int num_disp, int num_rows, int num_cols);
 /* d_dc_wta.cu:9-35 */
 void orc_wta(const float *cost, float *disp, int num_disp, int zero_disp, int num_rows, int num_cols);
+/* four-direction scanline optimisation + WTA: PARITY UNPINNED (the reference's d_dc_hslo.cu is a stub); this is
+ * the specification of the stage, see s2mv_oracle.c */
+void orc_so(const float *cost, float *cost_out, float *disp, const uint8_t *img_own, const uint8_t *img_other,
+            int view, float T, float H1, float H2, int num_disp, int zero_disp, int num_rows, int num_cols, int elem_sz);
 /* d_dr_dcc.cu:18-128; outliers are overwritten (reference memsets them to 0 first) */
 void orc_dcc(uint8_t *outliers_l, uint8_t *outliers_r, const float *disp_l, const float *disp_r,
              int num_rows, int num_cols);

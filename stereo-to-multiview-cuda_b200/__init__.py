@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "s2mv_stream_open", "s2mv_stream_input_buffer", "s2mv_stream_submit", "s2mv_stream_collect",
     "s2mv_stream_pending", "s2mv_stream_close", "s2mv_set_chunk_sequential", "s2mv_is_chunk_sequential",
     "s2mv_configure_band", "s2mv_band_info", "s2mv_band_prepare", "s2mv_band_pass", "s2mv_band_halo",
-    "s2mv_band_disp", "s2mv_band_finish",
+    "s2mv_band_disp", "s2mv_band_finish", "s2mv_dc_so", "s2mv_enable_so",
 ]
 # the reference's own C++ symbols exported as shims (include/s2mv_compat.h)
 COMPAT_SYMBOLS = [
@@ -37,7 +37,7 @@ COMPAT_SYMBOLS = [
     "_Z8ca_crossPhPS_PPfS2_ffiiiiii", "_Z6dc_wtaPPfS_iiii", "_Z6dr_dccPhS_PfS0_ii",
     "_Z6dr_irvPfPhPS0_ifiiiiii", "_Z18filter_bilateral_1Pfiffiii", "_Z9dibr_occlPhS_PfS0_ii",
     "_Z14filter_bleed_1Phiii", "_Z17dibr_occl_to_maskPfS_PhS0_ii", "_Z17filter_gaussian_1Pfifii",
-    "_Z8dibr_dbmPhS_S_PfS0_S_S_S0_S0_fiii", "_Z13mux_multiviewPPhS_ifiiiii",
+    "_Z8dibr_dbmPhS_S_PfS0_S_S_S0_S0_fiii", "_Z13mux_multiviewPPhS_ifiiiii", "_Z7dc_hsloPPfS_PhS1_fffiiiii",
 ]
 
 
@@ -358,6 +358,21 @@ class Pipeline:
         disp = np.empty((H, W), np.float32)
         _check(self._L.s2mv_dc_wta(self._ctx, _ptr_table([cost[d] for d in range(D)]), _p(disp), D, zero_disp, H, W))
         return disp
+
+    def enable_so(self, on=True, T=15.0, H1=1.0, H2=3.0):
+        """Frame path: scanline optimisation between aggregation and WTA (off by default)."""
+        _check(self._L.s2mv_enable_so(self._ctx, int(on), _f(T), _f(H1), _f(H2)))
+
+    def dc_so(self, cost, img_own, img_other, view, T, H1, H2, zero_disp, want_cost=False):
+        """Scanline optimisation + WTA of one view's aggregated cost (the reference's unfinished dc_hslo)."""
+        cost = np.ascontiguousarray(cost, np.float32)
+        D, H, W = cost.shape
+        disp = np.empty((H, W), np.float32)
+        out, tout = self._cost_tables(D, H, W) if want_cost else (None, None)
+        _check(self._L.s2mv_dc_so(self._ctx, _ptr_table([cost[d] for d in range(D)]), _p(disp), tout,
+                                  _p(np.ascontiguousarray(img_own, np.uint8)), _p(np.ascontiguousarray(img_other, np.uint8)),
+                                  int(view), _f(T), _f(H1), _f(H2), D, zero_disp, H, W, 3))
+        return (disp, out) if want_cost else disp
 
     def dr_dcc(self, disp_l, disp_r):
         disp_l = np.ascontiguousarray(disp_l, np.float32)

@@ -21,6 +21,7 @@
 #include "kernels_line.cuh"
 #include "kernels_prep.cuh"
 #include "kernels_refine.cuh"
+#include "kernels_so.cuh"
 
 using namespace s2mv;
 
@@ -218,6 +219,8 @@ struct s2mv_ctx {
     // row-band mode (s2mv_band.inl): this context is a sub-image of a taller frame
     bool band = false;
     int band_frame_rows = 0, band_ly0 = 0, band_o0 = 0, band_o1 = 0, band_vlo = 0, band_vhi = 0;
+    bool so_on = false;        // scanline optimisation between aggregation and WTA (s2mv_enable_so)
+    float so_T = 15.f, so_H1 = 1.f, so_H2 = 3.f;
     int chunk_seq_mode = -1;  // -1 auto (when the full volumes do not fit), 0 never, 1 whenever D > 128
     s2mv_params prm;
     CostPlan plan;
@@ -443,6 +446,7 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
     c->prm = *p;
     c->plan = pl;
     c->band = band != nullptr;
+    if (c->so_on && (pl.nchunks != 1 || band)) c->so_on = false;  // only for num_disp <= 128, whole frames
     if (band) {
         c->band_frame_rows = band->frame_rows; c->band_ly0 = band->ly0; c->band_o0 = band->o0; c->band_o1 = band->o1;
         c->band_vlo = band->vlo; c->band_vhi = band->vhi;
@@ -532,6 +536,16 @@ extern "C" int s2mv_set_chunk_sequential(s2mv_ctx *c, int mode)
     return S2MV_OK;
 }
 extern "C" int s2mv_is_chunk_sequential(const s2mv_ctx *c) { return c && c->configured && c->plan.chunk_seq ? 1 : 0; }
+
+extern "C" int s2mv_enable_so(s2mv_ctx *c, int on, float T, float H1, float H2)
+{
+    if (!c) return fail(S2MV_ERR_BAD_PARAM, "null ctx");
+    if (on && c->configured && (c->plan.nchunks != 1 || c->band))
+        return fail(S2MV_ERR_BAD_PARAM, "scanline optimisation needs num_disp <= 128 and a whole-frame context");
+    c->so_on = on != 0;
+    c->so_T = T; c->so_H1 = H1; c->so_H2 = H2;
+    return S2MV_OK;
+}
 
 extern "C" int s2mv_enable_timing(s2mv_ctx *c, int on)
 {
@@ -687,6 +701,35 @@ static int launch_aggregate(s2mv_ctx *c, const LineArgs &a, float4 *A, float4 *B
     return S2MV_OK;
 }
 
+// Four-direction scanline optimisation of `nviews` aggregated volumes (slot v at cost + v * view_stride4)
+// into acc (same layout), then WTA into disp[] (kernels_so.cuh; specification: DESIGN.md §3.4, held to it by tests/test_so.py).
+static int launch_so(s2mv_ctx *c, const float4 *cost, float4 *acc, size_t view_stride4, float *const disp[2], int nviews,
+                     int view_first, float T, float H1, float H2, int D, int zd, int H, int W, bool store_cost,
+                     cudaStream_t st)
+{
+    const CostPlan &pl = c->plan;
+    if (pl.nchunks != 1) return fail(S2MV_ERR_BAD_PARAM, "scanline optimisation supports num_disp <= 128 (got %d)", D);
+    SoArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int v = 0; v < nviews; ++v) { a.cost[v] = cost + v * view_stride4; a.acc[v] = acc + v * view_stride4; a.disp[v] = disp[v]; }
+    a.pix[0] = c->pix[0]; a.pix[1] = c->pix[1];
+    a.H = H; a.W = W; a.D = D; a.zd = zd; a.LPtot = pl.LPtot; a.view_first = view_first;
+    a.T = T;
+    a.P1[0] = H1; a.P1[1] = H1 / 4.0f; a.P1[2] = H1 / 10.0f;   // d_dc_hslo.cu:124-127
+    a.P2[0] = H2; a.P2[1] = H2 / 4.0f; a.P2[2] = H2 / 10.0f;
+    a.store_cost = store_cost ? 1 : 0;
+    const int dirs[4][2] = {{+1, 0}, {-1, 0}, {0, +1}, {0, -1}};
+    for (int k = 0; k < 4; ++k) {
+        a.dx = dirs[k][0]; a.dy = dirs[k][1];
+        a.first = k == 0; a.last = k == 3;
+        const int nlines = a.dx ? H : W;
+        k_so_dir<<<dim3((nlines + 3) / 4, nviews), 128, 0, st>>>(a);
+        KCHECK();
+    }
+    c->launches += 4;
+    return S2MV_OK;
+}
+
 // CI + H, V, V, H + WTA for both views: A <- CI+H; B <- V(A); A <- V(B); disp <- WTA(H(A))
 static int launch_costvol(s2mv_ctx *c, float *dispL, float *dispR, cudaStream_t st)
 {
@@ -704,6 +747,13 @@ static int launch_costvol(s2mv_ctx *c, float *dispL, float *dispR, cudaStream_t 
     a.disp[0] = dispL; a.disp[1] = dispR;
     if (pl.nchunks > 1)
         for (int v = 0; v < 2; ++v) CU(cudaMemsetAsync(c->wta_key[v], 0xff, n * sizeof(unsigned long long), st));
+    if (c->so_on) {
+        // aggregated volume kept (pass 4 stores into B), scanline optimisation B -> A, WTA from there
+        float *disp[2] = {dispL, dispR};
+        TRY(launch_aggregate(c, a, A, B, view_stride4, 2, true, false, st));
+        TRY(launch_so(c, B, A, view_stride4, disp, 2, 0, c->so_T, c->so_H1, c->so_H2, p.num_disp, p.zero_disp, H, W, false, st));
+        return S2MV_OK;
+    }
     if (pl.chunk_seq) {
         for (int ch = 0; ch < pl.nchunks; ++ch) {
             a.d_first = ch * 4 * pl.LP;

@@ -62,6 +62,13 @@ void dc_wta(float **cost, float *disp, int num_disp, int zero_disp, int num_rows
     check(s2mv_dc_wta(nullptr, cost, disp, num_disp, zero_disp, num_rows, num_cols), "dc_wta");
 }
 
+void dc_hslo(float **cost, float *disp, unsigned char *img_l, unsigned char *img_r, float T, float H1, float H2,
+             int num_disp, int zero_disp, int num_rows, int num_cols, int elem_sz)
+{
+    check(s2mv_dc_so(nullptr, cost, disp, nullptr, img_l, img_r, 0, T, H1, H2, num_disp, zero_disp, num_rows, num_cols,
+                     elem_sz), "dc_hslo");
+}
+
 void dr_dcc(unsigned char *outliers_l, unsigned char *outliers_r, float *disp_l, float *disp_r, int num_rows,
             int num_cols)
 {

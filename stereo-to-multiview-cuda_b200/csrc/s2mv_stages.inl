@@ -218,6 +218,50 @@ extern "C" int s2mv_dc_wta(s2mv_ctx *ctx, float **cost, float *disp, int D, int 
     return S2MV_OK;
 }
 
+// the stage the reference declares as dc_hslo (d_dc_hslo.cu:97-101): scanline optimisation of one view's
+// aggregated cost + WTA.  PARITY UNPINNED (stub in the reference); specification: DESIGN.md §3.4.
+extern "C" int s2mv_dc_so(s2mv_ctx *ctx, float **cost, float *disp, float **cost_out, const uint8_t *img_own,
+                          const uint8_t *img_other, int view, float T, float H1, float H2, int D, int zd, int H, int W,
+                          int elem_sz)
+{
+    if (!cost || !img_own || !img_other || (!disp && !cost_out)) return fail(S2MV_ERR_BAD_PARAM, "null argument");
+    if (elem_sz != 3) return fail(S2MV_ERR_BAD_PARAM, "elem_sz must be 3");
+    if (view < 0 || view > 1) return fail(S2MV_ERR_BAD_PARAM, "view must be 0 (left) or 1 (right)");
+    s2mv_ctx *c;
+    TRY(acquire(ctx, H, W, D, zd, ctx && ctx->configured ? ctx->prm.usd : 17, &c));
+    TRY(need_full_volume(c));
+    const CostPlan &pl = c->plan;
+    cudaStream_t st = c->stream;
+    const size_t n = (size_t)H * W;
+    Tmp planes, d_own, d_oth;
+    TRY(planes.alloc((size_t)D * n * sizeof(float)));
+    TRY(d_own.alloc(n * 3));
+    TRY(d_oth.alloc(n * 3));
+    for (int d = 0; d < D; ++d) TRY(upload(planes.as<float>() + (size_t)d * n, cost[d], n * sizeof(float), st));
+    TRY(upload(d_own.p, img_own, n * 3, st));
+    TRY(upload(d_oth.p, img_other, n * 3, st));
+    // pix[0] = left image, pix[1] = right image
+    const uint8_t *dl = view == 0 ? d_own.as<uint8_t>() : d_oth.as<uint8_t>();
+    const uint8_t *dr = view == 0 ? d_oth.as<uint8_t>() : d_own.as<uint8_t>();
+    dim3 g((W + 255) / 256, H);
+    k_unpack<<<g, 256, 0, st>>>(dl, dr, (size_t)W * 3, c->pix[0], c->pix[1], c->gray[0], c->gray[1], nullptr, nullptr, H, W);
+    KCHECK();
+    dim3 gt((unsigned)((n + 31) / 32), (pl.Dp + 31) / 32);
+    k_planes_to_vol<<<gt, dim3(32, 8), 0, st>>>(planes.as<float>(), c->vol[0], D, pl.Dp, n);
+    KCHECK();
+    float *dv[2] = {disp ? c->disp[0] : nullptr, nullptr};
+    TRY(launch_so(c, reinterpret_cast<const float4 *>(c->vol[0]), reinterpret_cast<float4 *>(c->vol[1]), 0, dv, 1, view, T,
+                  H1, H2, D, zd, H, W, cost_out != nullptr, st));
+    if (disp) TRY(download(disp, c->disp[0], n * sizeof(float), st));
+    if (cost_out) {
+        k_vol_to_planes<<<gt, dim3(32, 8), 0, st>>>(c->vol[1], planes.as<float>(), D, pl.Dp, n);
+        KCHECK();
+        for (int d = 0; d < D; ++d) TRY(download(cost_out[d], planes.as<float>() + (size_t)d * n, n * sizeof(float), st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return S2MV_OK;
+}
+
 extern "C" int s2mv_dr_dcc(s2mv_ctx *ctx, uint8_t *outliers_l, uint8_t *outliers_r, const float *disp_l,
                            const float *disp_r, int H, int W)
 {
