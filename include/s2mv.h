@@ -96,6 +96,16 @@ int s2mv_process_sbs(s2mv_ctx *ctx, const uint8_t *img_sbs, int num_cols_sbs,
 int s2mv_process_sbs_device(s2mv_ctx *ctx, const uint8_t *d_img_sbs, int num_cols_sbs,
                             float *d_disp_l, float *d_disp_r, uint8_t *d_interlaced, void *stream);
 
+/* Two-resolution variant = adcensus_stm_2 (d_io.cu:240-508, d_tx_scale.cu:8-52): both views are scaled down
+ * bilinearly to num_rows_disp x num_cols_disp, disparities are estimated and refined there, scaled back up
+ * (bilinear, x 1/disp_scale) and drive DIBR + interlace at full resolution.  disp_l / disp_r are the
+ * FULL-resolution maps.  s2mv_configure_2 replaces s2mv_configure for such a context. */
+int s2mv_configure_2(s2mv_ctx *ctx, const s2mv_params *p, int num_rows_disp, int num_cols_disp, float disp_scale);
+int s2mv_process_sbs_2(s2mv_ctx *ctx, const uint8_t *img_sbs, int num_cols_sbs,
+                       float *disp_l, float *disp_r, uint8_t *interlaced);
+int s2mv_process_sbs_2_device(s2mv_ctx *ctx, const uint8_t *d_img_sbs, int num_cols_sbs,
+                              float *d_disp_l, float *d_disp_r, uint8_t *d_interlaced, void *stream);
+
 /* Cost-volume leg only: cost initialisation + 4-pass cross aggregation + WTA,
  * both views (the MDE/s metric; BASELINE config 5).  Device pointers. */
 int s2mv_costvol_device(s2mv_ctx *ctx, const uint8_t *d_img_sbs, int num_cols_sbs,

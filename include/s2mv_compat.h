@@ -15,6 +15,12 @@ void adcensus_stm(unsigned char *img_sbs, float *disp_l, float *disp_r, unsigned
                   int num_rows, int num_cols_sbs, int num_cols, int num_rows_out, int num_cols_out, int elem_sz,
                   int num_views, int angle, int num_disp, int zero_disp, float ad_coeff, float census_coeff,
                   float ucd, float lcd, int usd, int lsd, int thresh_s, float thresh_h);
+/* d_io.h:42-53   _Z14adcensus_stm_2PhPfS0_S_iiiiiiiifiiiiffffiiif  (half-resolution variant, d_io.cu:240-508) */
+void adcensus_stm_2(unsigned char *img_sbs, float *disp_l, float *disp_r, unsigned char *interlaced, int num_rows,
+                    int num_cols_sbs, int num_cols, int num_rows_out, int num_cols_out, int num_rows_disp,
+                    int num_cols_disp, int elem_sz, float disp_scale, int num_views, int angle, int num_disp,
+                    int zero_disp, float ad_coeff, float census_coeff, float ucd, float lcd, int usd, int lsd,
+                    int thresh_s, float thresh_h);
 /* d_ci_adcensus.h  _Z11ci_adcensusPhS_PPfS1_ffiiiii */
 void ci_adcensus(unsigned char *img_l, unsigned char *img_r, float **cost_l, float **cost_r, float ad_coeff,
                  float census_coeff, int num_disp, int zero_disp, int num_rows, int num_cols, int elem_sz);

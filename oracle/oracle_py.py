@@ -294,3 +294,32 @@ def adcensus_stm(sbs, W, Ho, Wo, num_views=8, angle=18, D=64, zd=32, ad_coeff=10
     if want_taps:
         return dl, dr, out, keep
     return dl, dr, out
+
+
+def scale_bilinear(img, out_rows, out_cols):
+    H, W, es = img.shape
+    out = np.zeros((out_rows, out_cols, es), np.uint8)
+    lib().orc_scale_bilinear(_p(np.ascontiguousarray(img)), _p(out), H, W, out_rows, out_cols, es)
+    return out
+
+
+def disp_scale(disp, out_rows, out_cols, scale):
+    H, W = disp.shape
+    out = np.zeros((out_rows, out_cols), np.float32)
+    lib().orc_disp_scale(_p(out), _p(np.ascontiguousarray(disp, np.float32)), out_rows, out_cols, H, W, _f(scale))
+    return out
+
+
+def adcensus_stm_2(sbs, W, Ho, Wo, Hd, Wd, disp_scale, num_views=8, angle=18, D=64, zd=32, ad_coeff=10.0,
+                   census_coeff=30.0, ucd=20.0, lcd=6.0, usd=17, lsd=9, thresh_s=20, thresh_h=0.4, luts=None):
+    """adcensus_stm_2 (d_io.cu:240-508) -> (disp_l, disp_r at full resolution, interlaced)."""
+    sbs = np.ascontiguousarray(sbs, np.uint8)
+    H, Ws, es = sbs.shape
+    dl = np.zeros((H, W), np.float32)
+    dr = np.zeros((H, W), np.float32)
+    out = np.zeros((Ho, Wo, es), np.uint8)
+    la, lc = (None, None) if luts is None else luts
+    lib().orc_adcensus_stm_2(_p(sbs), _p(dl), _p(dr), _p(out), H, Ws, W, Ho, Wo, Hd, Wd, es, _f(disp_scale),
+                             num_views, int(angle), D, zd, _f(ad_coeff), _f(census_coeff), _f(ucd), _f(lcd), usd, lsd,
+                             thresh_s, _f(thresh_h), _p(la), _p(lc))
+    return dl, dr, out

@@ -894,3 +894,122 @@ void orc_adcensus_stm(const uint8_t *img_sbs, float *disp_l, float *disp_r, uint
     free(occl_l); free(occl_r); free(mask_l); free(mask_r);
     free(img_l); free(img_r);
 }
+
+/* ------------------------------------------------ half-resolution variant */
+/* alu_bilinear_interp / alu_bilinear_interp_f (d_alu.cu:17-71) with the fma placement nvcc gives them at
+ * -O3 (PTX of d_alu.cu: top = fma(1-wx, v00, wx*v01), bot likewise, res = fma(1-wy, top, wy*bot)). */
+static inline float orc_bilerp(float v00, float v01, float v10, float v11, float wx, float wy)
+{
+    float iwx = 1.0f - wx, iwy = 1.0f - wy;
+    float top = fmaf(iwx, v00, wx * v01);
+    float bot = fmaf(iwx, v10, wx * v11);
+    return fmaf(iwy, top, wy * bot);
+}
+
+static inline float orc_sample_coord(int t, int out_n, int in_n)
+{
+    /* d_tx_scale.cu:19-20,41-42: fmin(fmax(((float) t / (float) out_n) * (float) in_n, 0), (float)(in_n - 1)) */
+    float v = ((float)t / (float)out_n) * (float)in_n;
+    v = v < 0.0f ? 0.0f : v;
+    return v > (float)(in_n - 1) ? (float)(in_n - 1) : v;
+}
+
+/* tx_scale_bilinear_kernel (d_tx_scale.cu:30-52) */
+void orc_scale_bilinear(const uint8_t *img_in, uint8_t *img_out, int in_rows, int in_cols, int out_rows, int out_cols,
+                        int elem_sz)
+{
+#pragma omp parallel for schedule(static)
+    for (int gy = 0; gy < out_rows; ++gy)
+        for (int gx = 0; gx < out_cols; ++gx) {
+            float xs = orc_sample_coord(gx, out_cols, in_cols), ys = orc_sample_coord(gy, out_rows, in_rows);
+            int x0 = (int)floorf(xs), y0 = (int)floorf(ys);
+            int x1 = imin(x0 + 1, in_cols - 1), y1 = imin(y0 + 1, in_rows - 1);
+            float wx = xs - (float)x0, wy = ys - (float)y0;
+            for (int c = 0; c < 3; ++c) {
+                float v00 = img_in[((size_t)y0 * in_cols + x0) * elem_sz + c], v01 = img_in[((size_t)y0 * in_cols + x1) * elem_sz + c];
+                float v10 = img_in[((size_t)y1 * in_cols + x0) * elem_sz + c], v11 = img_in[((size_t)y1 * in_cols + x1) * elem_sz + c];
+                img_out[((size_t)gy * out_cols + gx) * elem_sz + c] = (uint8_t)(unsigned int)orc_bilerp(v00, v01, v10, v11, wx, wy);
+            }
+        }
+}
+
+/* tx_disp_scale_kernel (d_tx_scale.cu:8-28) */
+void orc_disp_scale(float *disp_out, const float *disp_in, int out_rows, int out_cols, int in_rows, int in_cols, float scale)
+{
+#pragma omp parallel for schedule(static)
+    for (int ty = 0; ty < out_rows; ++ty)
+        for (int tx = 0; tx < out_cols; ++tx) {
+            float xs = orc_sample_coord(tx, out_cols, in_cols), ys = orc_sample_coord(ty, out_rows, in_rows);
+            int x0 = (int)floorf(xs), y0 = (int)floorf(ys);
+            int x1 = imin(x0 + 1, in_cols - 1), y1 = imin(y0 + 1, in_rows - 1);
+            float wx = xs - (float)x0, wy = ys - (float)y0;
+            float v = orc_bilerp(disp_in[(size_t)y0 * in_cols + x0], disp_in[(size_t)y0 * in_cols + x1],
+                                 disp_in[(size_t)y1 * in_cols + x0], disp_in[(size_t)y1 * in_cols + x1], wx, wy);
+            disp_out[(size_t)ty * out_cols + tx] = v * scale;
+        }
+}
+
+/* adcensus_stm_2 (d_io.cu:240-508): disparity estimation on bilinearly down-scaled images, disparities scaled
+ * back up (x 1/disp_scale), DIBR + interlace at full resolution.  disp_l / disp_r are the FULL-resolution maps. */
+void orc_adcensus_stm_2(const uint8_t *img_sbs, float *disp_l, float *disp_r, uint8_t *interlaced,
+                        int num_rows, int num_cols_sbs, int num_cols, int num_rows_out, int num_cols_out,
+                        int num_rows_disp, int num_cols_disp, int elem_sz, float disp_scale,
+                        int num_views, int angle, int num_disp, int zero_disp,
+                        float ad_coeff, float census_coeff, float ucd, float lcd, int usd, int lsd,
+                        int thresh_s, float thresh_h, const float *lut_ad, const float *lut_cen)
+{
+    size_t plane = (size_t)num_rows * num_cols, imgsz = plane * elem_sz;
+    size_t dplane = (size_t)num_rows_disp * num_cols_disp;
+    uint8_t *img_l = (uint8_t *)malloc(imgsz), *img_r = (uint8_t *)malloc(imgsz);
+    orc_demux_sbs(img_sbs, img_l, img_r, num_rows, num_cols_sbs, num_cols, elem_sz);
+    uint8_t *low_l = (uint8_t *)malloc(dplane * elem_sz), *low_r = (uint8_t *)malloc(dplane * elem_sz);
+    orc_scale_bilinear(img_l, low_l, num_rows, num_cols, num_rows_disp, num_cols_disp, elem_sz);
+    orc_scale_bilinear(img_r, low_r, num_rows, num_cols, num_rows_disp, num_cols_disp, elem_sz);
+
+    float *cost_l = (float *)malloc(sizeof(float) * dplane * num_disp);
+    float *cost_r = (float *)malloc(sizeof(float) * dplane * num_disp);
+    uint8_t *arms_l = (uint8_t *)malloc(4 * dplane), *arms_r = (uint8_t *)malloc(4 * dplane);
+    float *dl = (float *)malloc(sizeof(float) * dplane), *dr = (float *)malloc(sizeof(float) * dplane);
+    orc_ci_adcensus(low_l, low_r, cost_l, cost_r, lut_ad, lut_cen, ad_coeff, census_coeff,
+                    num_disp, zero_disp, num_rows_disp, num_cols_disp, elem_sz);
+    orc_cross_arms(low_l, arms_l, ucd, lcd, usd, lsd, num_rows_disp, num_cols_disp, elem_sz);
+    orc_ca_aggregate(cost_l, arms_l, num_disp, num_rows_disp, num_cols_disp);
+    orc_cross_arms(low_r, arms_r, ucd, lcd, usd, lsd, num_rows_disp, num_cols_disp, elem_sz);
+    orc_ca_aggregate(cost_r, arms_r, num_disp, num_rows_disp, num_cols_disp);
+    orc_wta(cost_l, dl, num_disp, zero_disp, num_rows_disp, num_cols_disp);
+    orc_wta(cost_r, dr, num_disp, zero_disp, num_rows_disp, num_cols_disp);
+    free(cost_l); free(cost_r);
+    uint8_t *out_l = (uint8_t *)malloc(dplane), *out_r = (uint8_t *)malloc(dplane);
+    orc_dcc(out_l, out_r, dl, dr, num_rows_disp, num_cols_disp);
+    orc_irv(dl, out_l, arms_l, thresh_s, thresh_h, num_rows_disp, num_cols_disp, num_disp, zero_disp, usd, 5, 0);
+    orc_irv(dr, out_r, arms_r, thresh_s, thresh_h, num_rows_disp, num_cols_disp, num_disp, zero_disp, usd, 5, 0);
+    orc_bilateral(dl, 7, 5, 10, num_rows_disp, num_cols_disp, num_disp);
+    orc_bilateral(dr, 7, 5, 10, num_rows_disp, num_cols_disp, num_disp);
+    free(out_l); free(out_r); free(arms_l); free(arms_r); free(low_l); free(low_r);
+    /* d_io.cu:425-426: scale factor 1.0f / disp_scale */
+    orc_disp_scale(disp_l, dl, num_rows, num_cols, num_rows_disp, num_cols_disp, 1.0f / disp_scale);
+    orc_disp_scale(disp_r, dr, num_rows, num_cols, num_rows_disp, num_cols_disp, 1.0f / disp_scale);
+    free(dl); free(dr);
+
+    uint8_t *occl_l = (uint8_t *)malloc(plane), *occl_r = (uint8_t *)malloc(plane);
+    float *mask_l = (float *)malloc(sizeof(float) * plane), *mask_r = (float *)malloc(sizeof(float) * plane);
+    orc_occl(occl_l, occl_r, disp_l, disp_r, num_rows, num_cols);
+    orc_bleed(occl_l, 1, num_rows, num_cols);
+    orc_bleed(occl_r, 1, num_rows, num_cols);
+    orc_occl_to_mask(mask_l, occl_l, num_rows, num_cols);
+    orc_occl_to_mask(mask_r, occl_r, num_rows, num_cols);
+    uint8_t *views_mem = (uint8_t *)calloc(imgsz * (size_t)num_views, 1);
+    const uint8_t **views = (const uint8_t **)malloc(sizeof(uint8_t *) * num_views);
+    views[0] = img_r;
+    views[num_views - 1] = img_l;
+    for (int v = 1; v < num_views - 1; ++v) {
+        float shift = (float)(1.0 - ((1.0 * (double)(float)v) / ((double)(float)num_views - 1.0)));
+        uint8_t *dst = views_mem + (size_t)v * imgsz;
+        orc_dbm(dst, img_l, img_r, disp_l, disp_r, mask_l, mask_r, shift, 10, 15.0f, num_rows, num_cols, elem_sz);
+        views[v] = dst;
+    }
+    orc_mux_multiview(views, interlaced, num_views, (float)angle, num_rows, num_cols, num_rows_out, num_cols_out, elem_sz, 2);
+    free(views); free(views_mem);
+    free(occl_l); free(occl_r); free(mask_l); free(mask_r);
+    free(img_l); free(img_r);
+}

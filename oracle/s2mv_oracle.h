@@ -140,4 +140,17 @@ int orc_max_threads(void);
 #ifdef __cplusplus
 }
 #endif
+
+/* half-resolution variant: tx_scale_bilinear_kernel, tx_disp_scale_kernel (d_tx_scale.cu:8-52), adcensus_stm_2
+ * (d_io.cu:240-508) */
+void orc_scale_bilinear(const uint8_t *img_in, uint8_t *img_out, int in_rows, int in_cols, int out_rows, int out_cols,
+                        int elem_sz);
+void orc_disp_scale(float *disp_out, const float *disp_in, int out_rows, int out_cols, int in_rows, int in_cols, float scale);
+void orc_adcensus_stm_2(const uint8_t *img_sbs, float *disp_l, float *disp_r, uint8_t *interlaced,
+                        int num_rows, int num_cols_sbs, int num_cols, int num_rows_out, int num_cols_out,
+                        int num_rows_disp, int num_cols_disp, int elem_sz, float disp_scale,
+                        int num_views, int angle, int num_disp, int zero_disp,
+                        float ad_coeff, float census_coeff, float ucd, float lcd, int usd, int lsd,
+                        int thresh_s, float thresh_h, const float *lut_ad, const float *lut_cen);
+
 #endif

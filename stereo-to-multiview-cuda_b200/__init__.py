@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = [
     "s2mv_stream_pending", "s2mv_stream_close", "s2mv_set_chunk_sequential", "s2mv_is_chunk_sequential",
     "s2mv_configure_band", "s2mv_band_info", "s2mv_band_prepare", "s2mv_band_pass", "s2mv_band_halo",
     "s2mv_band_disp", "s2mv_band_finish", "s2mv_dc_so", "s2mv_enable_so",
+    "s2mv_configure_2", "s2mv_process_sbs_2", "s2mv_process_sbs_2_device",
 ]
 # the reference's own C++ symbols exported as shims (include/s2mv_compat.h)
 COMPAT_SYMBOLS = [
@@ -38,6 +39,7 @@ COMPAT_SYMBOLS = [
     "_Z6dr_irvPfPhPS0_ifiiiiii", "_Z18filter_bilateral_1Pfiffiii", "_Z9dibr_occlPhS_PfS0_ii",
     "_Z14filter_bleed_1Phiii", "_Z17dibr_occl_to_maskPfS_PhS0_ii", "_Z17filter_gaussian_1Pfifii",
     "_Z8dibr_dbmPhS_S_PfS0_S_S_S0_S0_fiii", "_Z13mux_multiviewPPhS_ifiiiii", "_Z7dc_hsloPPfS_PhS1_fffiiiii",
+    "_Z14adcensus_stm_2PhPfS0_S_iiiiiiiifiiiiffffiiif",
 ]
 
 
@@ -153,6 +155,26 @@ class Pipeline:
         _check(self._L.s2mv_configure(self._ctx, C.byref(p)))
         self.params = p
         return self
+
+    def configure_2(self, num_rows_disp, num_cols_disp, disp_scale, **params):
+        """Two-resolution context (adcensus_stm_2): estimation at num_rows_disp x num_cols_disp."""
+        p = default_params(**params)
+        _check(self._L.s2mv_configure_2(self._ctx, C.byref(p), int(num_rows_disp), int(num_cols_disp), _f(disp_scale)))
+        self.params = p
+        return self
+
+    def adcensus_stm_2(self, img_sbs):
+        """adcensus_stm_2 (d_io.cu:240-508): host arrays in/out, synchronous; full-resolution disparities."""
+        p = self.params
+        img_sbs = np.ascontiguousarray(img_sbs, np.uint8)
+        H, Ws, es = img_sbs.shape
+        if H != p.num_rows or es != 3:
+            raise S2mvError("frame shape does not match the configured size")
+        dl = np.empty((H, p.num_cols), np.float32)
+        dr = np.empty((H, p.num_cols), np.float32)
+        out = np.empty((p.num_rows_out, p.num_cols_out, 3), np.uint8)
+        _check(self._L.s2mv_process_sbs_2(self._ctx, _p(img_sbs), Ws, _p(dl), _p(dr), _p(out)))
+        return dl, dr, out
 
     def set_chunk_sequential(self, mode):
         """-1 auto / 0 never / 1 always (num_disp > 128): one 128-disparity chunk of the volumes resident at a

@@ -220,6 +220,58 @@ k_arms_tile(const uint32_t *__restrict__ pix0, const uint32_t *__restrict__ pix1
     arms[(size_t)y * W + x] = (uint32_t)u | ((uint32_t)d << 8) | ((uint32_t)l << 16) | ((uint32_t)r << 24);
 }
 
+// ---- half-resolution variant (adcensus_stm_2, d_io.cu:240-508) -------------
+// alu_bilinear_interp / alu_bilinear_interp_f (d_alu.cu:17-71) as nvcc -O3 compiles them:
+// top = fma(1-wx, v00, wx*v01), bot likewise, res = fma(1-wy, top, wy*bot).
+__device__ __forceinline__ float bilerp_ref(float v00, float v01, float v10, float v11, float wx, float wy)
+{
+    const float iwx = __fsub_rn(1.0f, wx), iwy = __fsub_rn(1.0f, wy);
+    const float top = __fmaf_rn(iwx, v00, __fmul_rn(wx, v01));
+    const float bot = __fmaf_rn(iwx, v10, __fmul_rn(wx, v11));
+    return __fmaf_rn(iwy, top, __fmul_rn(wy, bot));
+}
+// d_tx_scale.cu:19-20,41-42: fmin(fmax(((float) t / (float) out_n) * (float) in_n, 0), (float)(in_n - 1))
+__device__ __forceinline__ float sample_coord_ref(int t, int out_n, int in_n)
+{
+    const float v = __fmul_rn(__fdiv_rn((float)t, (float)out_n), (float)in_n);
+    return fminf(fmaxf(v, 0.0f), (float)(in_n - 1));
+}
+
+// tx_scale_bilinear_kernel (d_tx_scale.cu:30-52): tightly packed BGR in, tightly packed BGR out
+__global__ void __launch_bounds__(256)
+k_scale_bilinear_bgr(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int in_rows, int in_cols, int out_rows,
+                     int out_cols)
+{
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x, gy = blockIdx.y;
+    if (gx >= out_cols || gy >= out_rows) return;
+    const float xs = sample_coord_ref(gx, out_cols, in_cols), ys = sample_coord_ref(gy, out_rows, in_rows);
+    const int x0 = (int)floorf(xs), y0 = (int)floorf(ys);
+    const int x1 = min(x0 + 1, in_cols - 1), y1 = min(y0 + 1, in_rows - 1);
+    const float wx = __fsub_rn(xs, (float)x0), wy = __fsub_rn(ys, (float)y0);
+    const uint8_t *p00 = in + ((size_t)y0 * in_cols + x0) * 3, *p01 = in + ((size_t)y0 * in_cols + x1) * 3;
+    const uint8_t *p10 = in + ((size_t)y1 * in_cols + x0) * 3, *p11 = in + ((size_t)y1 * in_cols + x1) * 3;
+    uint8_t *o = out + ((size_t)gy * out_cols + gx) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        o[c] = (uint8_t)__float2uint_rz(bilerp_ref((float)p00[c], (float)p01[c], (float)p10[c], (float)p11[c], wx, wy));
+}
+
+// tx_disp_scale_kernel (d_tx_scale.cu:8-28)
+__global__ void __launch_bounds__(256)
+k_disp_scale(float *__restrict__ out, const float *__restrict__ in, int out_rows, int out_cols, int in_rows, int in_cols,
+             float scale)
+{
+    const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y;
+    if (tx >= out_cols || ty >= out_rows) return;
+    const float xs = sample_coord_ref(tx, out_cols, in_cols), ys = sample_coord_ref(ty, out_rows, in_rows);
+    const int x0 = (int)floorf(xs), y0 = (int)floorf(ys);
+    const int x1 = min(x0 + 1, in_cols - 1), y1 = min(y0 + 1, in_rows - 1);
+    const float wx = __fsub_rn(xs, (float)x0), wy = __fsub_rn(ys, (float)y0);
+    const float v = bilerp_ref(in[(size_t)y0 * in_cols + x0], in[(size_t)y0 * in_cols + x1], in[(size_t)y1 * in_cols + x0],
+                               in[(size_t)y1 * in_cols + x1], wx, wy);
+    out[(size_t)ty * out_cols + tx] = __fmul_rn(v, scale);
+}
+
 // packed arms <-> the reference's four byte planes (UP, DOWN, LEFT, RIGHT)
 __global__ void k_arms_unpack(const uint32_t *__restrict__ arms, uint8_t *__restrict__ planes, size_t n)
 {

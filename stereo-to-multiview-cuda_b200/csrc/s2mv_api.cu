@@ -219,6 +219,12 @@ struct s2mv_ctx {
     // row-band mode (s2mv_band.inl): this context is a sub-image of a taller frame
     bool band = false;
     int band_frame_rows = 0, band_ly0 = 0, band_o0 = 0, band_o1 = 0, band_vlo = 0, band_vhi = 0;
+    // two-resolution mode (adcensus_stm_2): this context works at full resolution (no cost volumes), `lo` is a
+    // whole context at the disparity resolution
+    s2mv_ctx *lo = nullptr;
+    bool no_volume = false;
+    uint8_t *lo_bgr[2] = {};
+    float disp_scale = 1.f;
     bool so_on = false;        // scanline optimisation between aggregation and WTA (s2mv_enable_so)
     float so_T = 15.f, so_H1 = 1.f, so_H2 = 3.f;
     int chunk_seq_mode = -1;  // -1 auto (when the full volumes do not fit), 0 never, 1 whenever D > 128
@@ -330,6 +336,7 @@ extern "C" int s2mv_create(s2mv_ctx **out, int device)
 extern "C" void s2mv_destroy(s2mv_ctx *c)
 {
     if (!c) return;
+    if (c->lo) { s2mv_destroy(c->lo); c->lo = nullptr; }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_arena(c);
@@ -418,7 +425,14 @@ static int build_luts(s2mv_ctx *c, float ad_coeff, float census_coeff, cudaStrea
 struct BandSpec { int frame_rows, ly0, o0, o1, vlo, vhi; };
 static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *band);
 
-extern "C" int s2mv_configure(s2mv_ctx *c, const s2mv_params *p) { return configure_impl(c, p, nullptr); }
+extern "C" int s2mv_configure(s2mv_ctx *c, const s2mv_params *p)
+{
+    if (c) {
+        if (c->lo) { s2mv_destroy(c->lo); c->lo = nullptr; }
+        c->no_volume = false;
+    }
+    return configure_impl(c, p, nullptr);
+}
 
 static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *band)
 {
@@ -469,7 +483,7 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
     }
     // a row band keeps only its own rows plus usd halo rows either side of the volumes
     const size_t vol_rows = band ? (size_t)(band->vhi - band->vlo) : (size_t)p->num_rows;
-    const size_t vol_elems = 2 * vol_rows * p->num_cols * (pl.chunk_seq ? 4 * pl.LP : pl.Dp);
+    const size_t vol_elems = c->no_volume ? 4 : 2 * vol_rows * p->num_cols * (pl.chunk_seq ? 4 * pl.LP : pl.Dp);
     for (int v = 0; v < 2; ++v) {
         TRY(dev_alloc_t(c, &c->pix[v], n));
         TRY(dev_alloc_t(c, &c->cen[v], n));
@@ -497,7 +511,7 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
         CU(cudaMemGetInfo(&free_b, &total_b));
         c->irv_hseg[0] = c->irv_hseg[1] = nullptr;
         c->irv_nbp = 0;
-        if (nbp <= 512 && 2.0 * (double)n * nbp < 0.25 * (double)free_b) {
+        if (!c->no_volume && nbp <= 512 && 2.0 * (double)n * nbp < 0.25 * (double)free_b) {
             TRY(dev_alloc_t(c, &c->irv_hseg[0], n * nbp));
             TRY(dev_alloc_t(c, &c->irv_hseg[1], n * nbp));
             c->irv_nbp = nbp;
@@ -932,10 +946,22 @@ static int launch_mux(s2mv_ctx *c, const uint8_t *const *views, uint8_t *out, in
 // --------------------------------------------------------- frame pipeline
 // Refinement (cross-check, region voting, bilateral; d_io.cu:139-151) and DIBR + interlace
 // (d_io.cu:160-236) from the WTA disparities in c->disp[].  Records timing events 3 and 4.
+static int run_dibr(s2mv_ctx *c, const float *fl, const float *fr, uint8_t *d_interlaced, cudaStream_t st);
+static int run_refine(s2mv_ctx *c, float *fl, float *fr, cudaStream_t st);
+
 static int run_refine_dibr(s2mv_ctx *c, float *d_disp_l, float *d_disp_r, uint8_t *d_interlaced, cudaStream_t st)
 {
+    float *fl = d_disp_l ? d_disp_l : c->dispF[0], *fr = d_disp_r ? d_disp_r : c->dispF[1];
+    TRY(run_refine(c, fl, fr, st));
+    if (c->timing) CU(cudaEventRecord(c->ev[3], st));
+    return run_dibr(c, fl, fr, d_interlaced, st);
+}
+
+// cross-check, region voting, bilateral (d_io.cu:139-151): c->disp[] -> fl / fr
+static int run_refine(s2mv_ctx *c, float *fl, float *fr, cudaStream_t st)
+{
     const s2mv_params &p = c->prm;
-    const int H = p.num_rows, W = p.num_cols, V = p.num_views;
+    const int H = p.num_rows, W = p.num_cols;
     const size_t n = (size_t)H * W;
     if (c->taps)
         for (int v = 0; v < 2; ++v)
@@ -955,15 +981,21 @@ static int run_refine_dibr(s2mv_ctx *c, float *d_disp_l, float *d_disp_r, uint8_
     if (c->taps)
         for (int v = 0; v < 2; ++v)
             CU(cudaMemcpyAsync(c->tap_irv[v], c->disp[v], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    float *fl = d_disp_l ? d_disp_l : c->dispF[0], *fr = d_disp_r ? d_disp_r : c->dispF[1];
     {
         const float *bin[2] = {c->disp[0], c->disp[1]};
         float *bout[2] = {fl, fr};
         TRY(launch_bilateral(c, bin, bout, 2, c->bil_spatial, c->bil_colour, p.bilateral_radius, p.num_disp, true, H, W,
                              st));
     }
-    if (c->timing) CU(cudaEventRecord(c->ev[3], st));
+    return S2MV_OK;
+}
 
+// DIBR + interlace (d_io.cu:160-236) from the refined disparities fl / fr.  Records timing event 4.
+static int run_dibr(s2mv_ctx *c, const float *fl, const float *fr, uint8_t *d_interlaced, cudaStream_t st)
+{
+    const s2mv_params &p = c->prm;
+    const int H = p.num_rows, W = p.num_cols, V = p.num_views;
+    const size_t n = (size_t)H * W;
     // DIBR (d_io.cu:160-191)
     CU(cudaMemsetAsync(c->occl[0], 0, n, st));
     CU(cudaMemsetAsync(c->occl[1], 0, n, st));
@@ -1008,6 +1040,7 @@ static int run_frame(s2mv_ctx *c, const uint8_t *d_sbs, int num_cols_sbs, float 
     const size_t n = (size_t)H * W;
     if (num_cols_sbs < 2 * W) return fail(S2MV_ERR_BAD_PARAM, "num_cols_sbs (%d) < 2*num_cols (%d)", num_cols_sbs, 2 * W);
     if (c->band) return fail(S2MV_ERR_BAD_PARAM, "this context is a row band: use the s2mv_band_* sequence");
+    if (c->no_volume) return fail(S2MV_ERR_BAD_PARAM, "this context is two-resolution (s2mv_configure_2): use s2mv_process_sbs_2*");
     c->launches = 0;
     if (c->timing) CU(cudaEventRecord(c->ev[0], st));
     // views[0] = right image, views[V-1] = left image (d_io.cu:181-182)
@@ -1051,11 +1084,16 @@ extern "C" int s2mv_costvol_device(s2mv_ctx *c, const uint8_t *d_img_sbs, int nu
                      stream ? (cudaStream_t)stream : c->stream);
 }
 
-extern "C" int s2mv_process_sbs(s2mv_ctx *c, const uint8_t *img_sbs, int num_cols_sbs, float *disp_l, float *disp_r,
-                                uint8_t *interlaced)
+static int run_frame_2(s2mv_ctx *c, const uint8_t *d_sbs, int num_cols_sbs, float *d_disp_l, float *d_disp_r,
+                       uint8_t *d_interlaced, cudaStream_t st);
+
+// host buffers in / out, synchronous: s2mv_process_sbs (adcensus_stm) and s2mv_process_sbs_2 (adcensus_stm_2)
+static int process_host(s2mv_ctx *c, const uint8_t *img_sbs, int num_cols_sbs, float *disp_l, float *disp_r,
+                        uint8_t *interlaced, bool two_res)
 {
     if (!c || !img_sbs) return fail(S2MV_ERR_BAD_PARAM, "null argument");
     if (!c->configured) return fail(S2MV_ERR_NOT_CONFIGURED, "call s2mv_configure first");
+    if (two_res && !c->lo) return fail(S2MV_ERR_NOT_CONFIGURED, "call s2mv_configure_2 first");
     CU(cudaSetDevice(c->device));
     const s2mv_params &p = c->prm;
     const size_t n = (size_t)p.num_rows * p.num_cols;
@@ -1097,7 +1135,8 @@ extern "C" int s2mv_process_sbs(s2mv_ctx *c, const uint8_t *img_sbs, int num_col
         memcpy(c->h_sbs, img_sbs, sbs_bytes);
         CU(cudaMemcpyAsync(c->sbs, c->h_sbs, sbs_bytes, cudaMemcpyHostToDevice, st));
     }
-    TRY(run_frame(c, c->sbs, num_cols_sbs, c->dispF[0], c->dispF[1], c->interlaced, false, st));
+    if (two_res) TRY(run_frame_2(c, c->sbs, num_cols_sbs, c->dispF[0], c->dispF[1], c->interlaced, st));
+    else TRY(run_frame(c, c->sbs, num_cols_sbs, c->dispF[0], c->dispF[1], c->interlaced, false, st));
     if (disp_l) CU(cudaMemcpyAsync(pin_dl ? disp_l : c->h_disp[0], c->dispF[0], n * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (disp_r) CU(cudaMemcpyAsync(pin_dr ? disp_r : c->h_disp[1], c->dispF[1], n * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (interlaced) CU(cudaMemcpyAsync(pin_out ? interlaced : c->h_interlaced, c->interlaced, out_bytes, cudaMemcpyDeviceToHost, st));
@@ -1106,6 +1145,18 @@ extern "C" int s2mv_process_sbs(s2mv_ctx *c, const uint8_t *img_sbs, int num_col
     if (disp_r && !pin_dr) memcpy(disp_r, c->h_disp[1], n * sizeof(float));
     if (interlaced && !pin_out) memcpy(interlaced, c->h_interlaced, out_bytes);
     return S2MV_OK;
+}
+
+extern "C" int s2mv_process_sbs(s2mv_ctx *c, const uint8_t *img_sbs, int num_cols_sbs, float *disp_l, float *disp_r,
+                                uint8_t *interlaced)
+{
+    return process_host(c, img_sbs, num_cols_sbs, disp_l, disp_r, interlaced, false);
+}
+
+extern "C" int s2mv_process_sbs_2(s2mv_ctx *c, const uint8_t *img_sbs, int num_cols_sbs, float *disp_l, float *disp_r,
+                                  uint8_t *interlaced)
+{
+    return process_host(c, img_sbs, num_cols_sbs, disp_l, disp_r, interlaced, true);
 }
 
 extern "C" int s2mv_get_exp_tables(s2mv_ctx *c, float ad_coeff, float census_coeff, float *lut_ad, float *lut_cen)
@@ -1183,3 +1234,4 @@ extern "C" int s2mv_read_taps(s2mv_ctx *c, float *wta_l, float *wta_r, uint8_t *
 #include "s2mv_stages.inl"
 #include "s2mv_stream.inl"
 #include "s2mv_band.inl"
+#include "s2mv_halfres.inl"

@@ -43,6 +43,35 @@ void adcensus_stm(unsigned char *img_sbs, float *disp_l, float *disp_r, unsigned
     check(s2mv_process_sbs(g_ctx, img_sbs, num_cols_sbs, disp_l, disp_r, interlaced), "adcensus_stm");
 }
 
+static s2mv_ctx *g_ctx2 = nullptr;
+static s2mv_params g_prm2;
+static int g_rows_disp = 0, g_cols_disp = 0;
+static float g_disp_scale = 0.f;
+
+void adcensus_stm_2(unsigned char *img_sbs, float *disp_l, float *disp_r, unsigned char *interlaced, int num_rows,
+                    int num_cols_sbs, int num_cols, int num_rows_out, int num_cols_out, int num_rows_disp,
+                    int num_cols_disp, int elem_sz, float disp_scale, int num_views, int angle, int num_disp,
+                    int zero_disp, float ad_coeff, float census_coeff, float ucd, float lcd, int usd, int lsd,
+                    int thresh_s, float thresh_h)
+{
+    s2mv_params p;
+    s2mv_default_params(&p);
+    p.num_rows = num_rows; p.num_cols = num_cols; p.num_rows_out = num_rows_out; p.num_cols_out = num_cols_out;
+    p.elem_sz = elem_sz; p.num_views = num_views; p.angle = angle; p.num_disp = num_disp; p.zero_disp = zero_disp;
+    p.ad_coeff = ad_coeff; p.census_coeff = census_coeff; p.ucd = ucd; p.lcd = lcd; p.usd = usd; p.lsd = lsd;
+    p.thresh_s = thresh_s; p.thresh_h = thresh_h;
+    if (!g_ctx2) {
+        check(s2mv_create(&g_ctx2, 0), "adcensus_stm_2");
+        memset(&g_prm2, 0, sizeof(g_prm2));
+    }
+    if (memcmp(&p, &g_prm2, sizeof(p)) != 0 || num_rows_disp != g_rows_disp || num_cols_disp != g_cols_disp ||
+        disp_scale != g_disp_scale) {
+        check(s2mv_configure_2(g_ctx2, &p, num_rows_disp, num_cols_disp, disp_scale), "adcensus_stm_2");
+        g_prm2 = p; g_rows_disp = num_rows_disp; g_cols_disp = num_cols_disp; g_disp_scale = disp_scale;
+    }
+    check(s2mv_process_sbs_2(g_ctx2, img_sbs, num_cols_sbs, disp_l, disp_r, interlaced), "adcensus_stm_2");
+}
+
 void ci_adcensus(unsigned char *img_l, unsigned char *img_r, float **cost_l, float **cost_r, float ad_coeff,
                  float census_coeff, int num_disp, int zero_disp, int num_rows, int num_cols, int elem_sz)
 {

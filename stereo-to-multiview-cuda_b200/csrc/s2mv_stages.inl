@@ -19,7 +19,7 @@ s2mv_ctx *g_stage_ctx = nullptr;
 int acquire(s2mv_ctx *user, int H, int W, int D, int zd, int usd, s2mv_ctx **out)
 {
     auto matches = [&](const s2mv_ctx *c) {
-        return c && c->configured && !c->band && c->prm.num_rows == H && c->prm.num_cols == W && c->prm.num_disp == D &&
+        return c && c->configured && !c->band && !c->no_volume && c->prm.num_rows == H && c->prm.num_cols == W && c->prm.num_disp == D &&
                c->prm.zero_disp == zd && c->prm.usd == usd;
     };
     if (matches(user)) { *out = user; return S2MV_OK; }
