@@ -136,17 +136,35 @@ k_irv_vote(const IrvArgs a)
         const uint32_t ac = arms[pix];
         const int cu = min(arm_up(ac), a.usd), nrows = cu + arm_down(ac) + 1;  // rows [-cu, +cd] inclusive
         int cnt = 0;
-        for (int r = lane; r < nrows; r += 32) {
-            const size_t row = (size_t)(gy - cu + r) * W;
-            const uint32_t ar = arms[row + gx];
+        // the arms of the support rows first (lane r <-> rows r, r + 32, ...; nrows <= 2*usd+1 <= 129), then one
+        // row per step with the lanes ACROSS its span: every row is one or two coalesced requests that do not
+        // depend on each other, instead of one lane walking a row pixel by pixel
+        uint32_t rarm[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const int r = lane + 32 * j;
+            rarm[j] = r < nrows ? arms[(size_t)(gy - cu + r) * W + gx] : 0u;
+        }
+#pragma unroll 8
+        for (int r = 0; r < nrows; ++r) {
+            const int rj = r >> 5;
+            const uint32_t pick = rj == 0 ? rarm[0] : (rj == 1 ? rarm[1] : (rj == 2 ? rarm[2] : (rj == 3 ? rarm[3] : rarm[4])));
+            const uint32_t ar = __shfl_sync(0xffffffffu, pick, r & 31);
             const int cl = arm_left(ar), span = cl + arm_right(ar) + 1;  // inclusive [-L, R]
-            const float *__restrict__ dp = disp + row + (gx - cl);
-            const uint8_t *__restrict__ op = outl + row + (gx - cl);
-#pragma unroll 4
-            for (int k = 0; k < span; ++k) {
-                const float dv = dp[k];
-                if (op[k] == 0) {
-                    atomicAdd(&hist[clampi((int)dv + a.zd, 0, a.nbins - 1)], 1);
+            const size_t row = (size_t)(gy - cu + r) * W + (gx - cl);
+            for (int k0 = 0; k0 < span; k0 += 32) {
+                const int k = k0 + lane;
+                // both loads issue together (the disparity is not waited for behind the outlier flag)
+                const bool in = k < span;
+                const uint8_t o = in ? outl[row + k] : (uint8_t)1;
+                const float dv = in ? disp[row + k] : 0.0f;
+                const bool valid = o == 0;
+                const int bin = clampi((int)dv + a.zd, 0, a.nbins - 1);
+                const unsigned act = __ballot_sync(0xffffffffu, valid);
+                if (valid) {
+                    // neighbours mostly vote for the same bin: one shared-memory add per distinct bin
+                    const unsigned same = __match_any_sync(act, bin);
+                    if (lane == __ffs(same) - 1) atomicAdd(&hist[bin], __popc(same));
                     ++cnt;
                 }
             }
