@@ -823,10 +823,10 @@ static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2],
     k_irv_compact<<<dim3((unsigned)((n + 4095) / 4096), nviews), 256, 0, st>>>(a);
     KCHECK();
     c->launches += 1;
-    // lists longer than 1/64 of the image take the dense path (decided on the device, per iteration and view)
+    // lists longer than 1/32 of the image take the dense path (decided on the device, per iteration and view)
     const bool dense_ok = c->irv_hseg[0] && c->irv_nbp >= a.nbins && (size_t)H * W == (size_t)c->prm.num_rows * c->prm.num_cols;
     a.nbp = c->irv_nbp;
-    a.dense_min = (int)(n / 64) + 1;
+    a.dense_min = (int)(n / 32) + 1;  // measured crossover of the two paths: a list of about n/28
     if (const char *e = getenv("S2MV_IRV_DENSE_MIN")) a.dense_min = atoi(e);  // test hook: 0 = always dense, huge = never
     for (int v = 0; v < nviews; ++v) a.hseg[v] = dense_ok ? c->irv_hseg[v] : nullptr;
     for (int it = 0; it < iterations; ++it) {
