@@ -55,6 +55,7 @@ struct IrvArgs {
     int *vote[2];        // accepted disparity or kNoVote, per list entry
     int *count[2];       // length of list
     int *next_count[2];  // length of next
+    int *ticket[2];      // next list entry to hand out (k_irv_vote_dense); reset by k_irv_apply
     int H, W, nbins, zd, usd, thresh_s;
     float thresh_h;
     // dense path (k_irv_hseg + k_irv_vote_dense): per-pixel histograms of the horizontal arm span
@@ -220,7 +221,10 @@ k_irv_hseg(const IrvArgs a)
     uint32_t *hw = reinterpret_cast<uint32_t *>(hs);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int gy = tile / tiles_x, bx = (tile - gy * tiles_x) * kHsegThreads;
-        for (int i = t; i < kHsegThreads * pitch / 4; i += kHsegThreads) hw[i] = 0u;
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(hs);  // kHsegThreads * pitch bytes is a multiple of 16
+            for (int i = t; i < kHsegThreads * pitch / 16; i += kHsegThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
         __syncthreads();
         const int gx = bx + t;
         if (gx < W) {
@@ -234,10 +238,13 @@ k_irv_hseg(const IrvArgs a)
                 if (op[k] == 0) mine[clampi((int)dp[k] + a.zd, 0, a.nbins - 1)] += 1;
         }
         __syncthreads();
+        // out: one pixel's nbp bytes per warp step, 128 bytes per store instruction, pointers walked by increments
         const int npix = min(kHsegThreads, W - bx);
-        uint32_t *__restrict__ dst = reinterpret_cast<uint32_t *>(hseg + ((size_t)gy * W + bx) * nbp);
-        for (int i = warp; i < npix; i += kHsegThreads / 32)
-            for (int w = lane; w < nbp / 4; w += 32) dst[(size_t)i * (nbp / 4) + w] = hw[i * (pitch / 4) + w];
+        const int wpp = nbp / 4, wps = pitch / 4;  // 32-bit words per pixel: global / shared
+        uint32_t *__restrict__ d = reinterpret_cast<uint32_t *>(hseg + ((size_t)gy * W + bx) * nbp) + (size_t)warp * wpp + lane;
+        const uint32_t *sp = hw + warp * wps + lane;
+        for (int i = warp; i < npix; i += kHsegThreads / 32, d += (kHsegThreads / 32) * wpp, sp += (kHsegThreads / 32) * wps)
+            for (int w = 0; w < wpp; w += 32) d[w] = sp[w];
         __syncthreads();
     }
 }
@@ -247,7 +254,7 @@ __global__ void __launch_bounds__(kIrvWarps * 32)
 k_irv_vote_dense(const IrvArgs a)
 {
     const int v = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     const int count = *a.count[v];
     if (count < a.dense_min) return;
     const float *__restrict__ disp = a.disp[v];
@@ -255,7 +262,17 @@ k_irv_vote_dense(const IrvArgs a)
     const uint32_t *__restrict__ hseg = reinterpret_cast<const uint32_t *>(a.hseg[v]);
     const int W = a.W;
     constexpr int WPP = 32 * NW;  // 32-bit words per pixel
-    for (int e = blockIdx.x * kIrvWarps + warp; e < count; e += gridDim.x * kIrvWarps) {
+    // Entries are handed out in list (= raster) order, 16 per ticket: the warps in flight then work on
+    // neighbouring image rows, whose span histograms they share through L2 (with a fixed stride per warp the
+    // uneven cost per entry lets the warps drift apart)
+    constexpr int kBatch = 16;
+    for (int e = 0, e_end = 0;; ++e) {
+        if (e == e_end) {
+            if (lane == 0) e = atomicAdd(a.ticket[v], kBatch);
+            e = __shfl_sync(0xffffffffu, e, 0);
+            e_end = min(e + kBatch, count);
+            if (e >= count) break;
+        }
         const int pix = a.list[v][e];
         const int gy = pix / W, gx = pix - gy * W;
         const uint32_t ac = arms[pix];
@@ -303,6 +320,7 @@ k_irv_apply(const IrvArgs a)
 {
     const int v = blockIdx.y;
     const int count = *a.count[v];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.ticket[v] = 0;  // for the next iteration's vote
     const int stride = gridDim.x * blockDim.x;
     for (int e0 = blockIdx.x * blockDim.x; e0 < count; e0 += stride) {  // block-uniform trip count
         const int e = e0 + threadIdx.x;

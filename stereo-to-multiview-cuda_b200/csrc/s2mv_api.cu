@@ -517,7 +517,7 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
             c->irv_nbp = nbp;
         }
     }
-    TRY(dev_alloc_t(c, &c->irv_count, 4));
+    TRY(dev_alloc_t(c, &c->irv_count, 8));
     TRY(dev_alloc_t(c, &c->tmask, n));
     TRY(dev_alloc_t(c, &c->lutAd, 768));
     TRY(dev_alloc_t(c, &c->lutCen, 68));
@@ -813,13 +813,14 @@ static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2],
         a.disp[v] = disp[v]; a.outliers[v] = outl[v]; a.arms[v] = arms[v];
         a.list[v] = c->irv_list[v]; a.next[v] = c->irv_list2[v]; a.vote[v] = c->irv_vote[v];
         a.count[v] = c->irv_count + v; a.next_count[v] = c->irv_count + 2 + v;
+        a.ticket[v] = c->irv_count + 4 + v;
     }
     a.H = H; a.W = W; a.nbins = D > 65 ? D : 65; a.zd = zd; a.usd = usd; a.thresh_s = thresh_s; a.thresh_h = thresh_h;
     const size_t hist_bytes = (size_t)kIrvWarps * a.nbins * sizeof(int);
     if (hist_bytes > 64 * 1024) return fail(S2MV_ERR_BAD_PARAM, "num_disp too large for the voting histogram");
     if (iterations <= 0) return S2MV_OK;
     // outliers -> list, once; every iteration then votes on its list and leaves the survivors as the next one
-    CU(cudaMemsetAsync(c->irv_count, 0, 4 * sizeof(int), st));
+    CU(cudaMemsetAsync(c->irv_count, 0, 8 * sizeof(int), st));
     k_irv_compact<<<dim3((unsigned)((n + 4095) / 4096), nviews), 256, 0, st>>>(a);
     KCHECK();
     c->launches += 1;
