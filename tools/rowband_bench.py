@@ -36,6 +36,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--check", action="store_true", help="compare with the single-context frame on rank 0")
     ap.add_argument("--baseline", action="store_true", help="also time the single-context frame on rank 0")
+    ap.add_argument("--sha", action="store_true", help="print SHA-256 of the assembled outputs (to compare runs whose "
+                                                       "single-context frame does not fit next to a band)")
+    ap.add_argument("--single", action="store_true", help="N = 1 only: time the ordinary single-context frame "
+                                                          "(chunk-sequential volumes when needed) instead of one band")
     args = ap.parse_args()
     rank, world, local_rank = sharding.dist_env()
     torch.cuda.set_device(local_rank)
@@ -45,6 +49,33 @@ def main():
     params = dict(num_rows=H, num_cols=W, num_disp=D, zero_disp=D // 2, num_views=8, angle=18, **bench.ALGO)
     sbs = synth.make_sbs(H, W, args.seed)
     d_sbs = torch.from_numpy(sbs).to(dev)
+
+    if args.single:
+        assert world == 1, "--single is the one-GPU reference run"
+        import hashlib
+        with s2mv_b200.Pipeline(local_rank, **params) as p:
+            d_dl = torch.empty((H, W), dtype=torch.float32, device=dev)
+            d_dr = torch.empty_like(d_dl)
+            d_out = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
+            st = torch.cuda.current_stream().cuda_stream
+            for _ in range(args.warmup):
+                p.process_device(d_sbs.data_ptr(), 2 * W, d_dl.data_ptr(), d_dr.data_ptr(), d_out.data_ptr(), st)
+            torch.cuda.synchronize()
+            t1 = 0.0
+            for _ in range(args.steps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                p.process_device(d_sbs.data_ptr(), 2 * W, d_dl.data_ptr(), d_dr.data_ptr(), d_out.data_ptr(), st)
+                b.record()
+                b.synchronize()
+                t1 += a.elapsed_time(b)
+            res = {"workload": f"synthetic {W}x{H} seed {args.seed}, D={D}, ONE context (no bands), full pipeline",
+                   "n_gpus": 1, "ms_per_frame": t1 / args.steps, "steps": args.steps, "arena_gb_per_gpu": p.arena_bytes / 1e9,
+                   "chunk_sequential": p.chunk_sequential,
+                   "sha": {k: hashlib.sha256(t.cpu().numpy().tobytes()).hexdigest() for k, t in
+                           (("disp_l", d_dl), ("disp_r", d_dr), ("interlaced", d_out))}}
+        print(json.dumps(res), flush=True)
+        return 0
 
     band = rowband.DistBand(local_rank, rank, world, **params)
     for _ in range(args.warmup):
@@ -70,6 +101,15 @@ def main():
                (D + 127) // 128 * 128 if D > 128 else 1 << (max(D, 4) - 1).bit_length()),
            "arena_gb_per_gpu": arena / 1e9, "transport": "torch.distributed NCCL send/recv + all_gather (disparity rows)"}
 
+    if args.sha:
+        import hashlib
+        sha = {}
+        for k, t in (("disp_l", out_l), ("disp_r", out_r), ("interlaced", out_i)):
+            full_t = rowband.allgather_rows_dist(t, band.bands, dist, torch) if world > 1 else t
+            if rank == 0:
+                sha[k] = hashlib.sha256(full_t.cpu().numpy().tobytes()).hexdigest()
+            del full_t
+        res["sha"] = sha
     if args.check or args.baseline:
         # assemble the frame on rank 0
         full = []
