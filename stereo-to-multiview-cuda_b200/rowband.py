@@ -270,24 +270,46 @@ class DistBand:
     def close(self):
         self.ctx.close()
 
-    def process(self, d_sbs, num_cols_sbs):
+    def process(self, d_sbs, num_cols_sbs, phases=None):
         """d_sbs: the whole SBS frame on this rank's GPU.  Returns this band's rows of
-        (disp_l, disp_r, interlaced); everything is enqueued on torch's current stream."""
+        (disp_l, disp_r, interlaced); everything is enqueued on torch's current stream.  `phases`: a dict that
+        receives the device time (ms) of every phase of this call (adds one synchronisation at the end)."""
         torch, dist, c = self.torch, self.dist, self.ctx
         st = torch.cuda.current_stream().cuda_stream
+        marks = []
+
+        def mark(name):
+            if phases is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+
+        mark("start")
         c.prepare(d_sbs.data_ptr(), num_cols_sbs, st)
+        mark("prepare")
         c.run_pass(1, st)
+        mark("pass1")
         if self.world > 1:
             exchange_halos_dist(lambda side, recv: [c.halo(1, v, side, recv) for v in (0, 1)], self.rank, self.world, dist)
+        mark("halo1")
         c.run_pass(2, st)
+        mark("pass2")
         if self.world > 1:
             exchange_halos_dist(lambda side, recv: [c.halo(2, v, side, recv) for v in (0, 1)], self.rank, self.world, dist)
+        mark("halo2")
         c.run_pass(3, st)
         c.run_pass(4, st)
+        mark("pass3+4")
         if self.world > 1:
             for v in (0, 1):
                 plane = c.disp_plane(v)
                 frame = allgather_rows_dist(plane[c.own_first:c.own_first + c.own_rows], self.bands, dist, torch)
                 plane.copy_(frame[c.local_y0:c.local_y0 + c.local_rows])
+        mark("gather")
         c.finish(self.out_l, self.out_r, self.out_i, st)
+        mark("finish")
+        if phases is not None:
+            marks[-1][1].synchronize()
+            for (_, a), (name, b) in zip(marks, marks[1:]):
+                phases[name] = phases.get(name, 0.0) + a.elapsed_time(b)
         return self.out_l, self.out_r, self.out_i

@@ -92,6 +92,13 @@ def main():
         b.synchronize()
         ms += sharding.reduce_scalar(a.elapsed_time(b), "max", dev)
     ms /= args.steps
+    phases = {}
+    band.process(d_sbs, 2 * W, phases)          # one more frame with per-phase device times (this rank's)
+    allph = [None] * world
+    if world > 1:
+        dist.all_gather_object(allph, phases)
+    else:
+        allph = [phases]
     arena = band.ctx.pipe.arena_bytes
     res = {"workload": f"config4-style: synthetic {W}x{H} seed {args.seed}, D={D}, one frame in {world} row band(s), "
                        "full pipeline (disparities + 8-view interlaced frame)",
@@ -99,6 +106,8 @@ def main():
            "band_rows": [y1 - y0 for y0, y1 in band.bands], "sub_image_rows": band.ctx.local_rows,
            "halo_rows": band.ctx.halo_rows, "halo_bytes_per_exchange_per_neighbour": 2 * band.ctx.halo_rows * W * 4 * (
                (D + 127) // 128 * 128 if D > 128 else 1 << (max(D, 4) - 1).bit_length()),
+           "phase_ms_max_over_ranks": {k: max(p[k] for p in allph) for k in phases},
+           "phase_ms_rank0": phases,
            "arena_gb_per_gpu": arena / 1e9, "transport": "torch.distributed NCCL send/recv + all_gather (disparity rows)"}
 
     if args.sha:
