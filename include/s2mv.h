@@ -149,6 +149,24 @@ int s2mv_band_pass(s2mv_ctx *ctx, int pass, void *stream);
 int s2mv_band_halo(s2mv_ctx *ctx, int after_pass, int view, int side, int recv, void **d_ptr, size_t *bytes);
 int s2mv_band_disp(s2mv_ctx *ctx, int view, float **d_plane);
 int s2mv_band_finish(s2mv_ctx *ctx, float *d_disp_l_band, float *d_disp_r_band, uint8_t *d_interlaced_band, void *stream);
+/* Peer-to-peer halos: once a band knows its neighbours' volumes -- another context of this process
+ * (s2mv_band_connect) or another process's GPU memory mapped through CUDA IPC (s2mv_band_ipc_export on the
+ * owner, s2mv_band_ipc_connect on the neighbour; one process per GPU, handles carried by any host channel) --
+ * passes 1 and 2 store the rows next to a band edge straight into the neighbour's halo rows over NVLink, from
+ * inside the producing kernel, and order themselves with an epoch word per neighbour on the stream.  The
+ * caller then exchanges no halos (s2mv_band_halo is not needed); every band of the frame must run the same
+ * pass sequence.  side 0 = the band above, 1 = the band below.  s2mv_band_status reports a neighbour that
+ * never arrived (it synchronises the stream). */
+typedef struct {
+    unsigned char mem[3][64];   /* cudaIpcMemHandle_t of volume A, volume B, the epoch words */
+    int frame_y0, frame_y1;     /* the band's own rows in the frame */
+    int local_y0, vlo, vrows;   /* sub-image origin, first volume row (local), volume rows */
+    int num_cols, lptot, frame_rows, device;
+} s2mv_band_ipc;
+int s2mv_band_connect(s2mv_ctx *ctx, int side, s2mv_ctx *neighbour);
+int s2mv_band_ipc_export(s2mv_ctx *ctx, s2mv_band_ipc *out);
+int s2mv_band_ipc_connect(s2mv_ctx *ctx, int side, const s2mv_band_ipc *neighbour);
+int s2mv_band_status(s2mv_ctx *ctx, void *stream);
 
 /* ---- asynchronous frame stream (the video loop, video_io.cpp:139-160) -----
  * The same frames through the same kernels as s2mv_process_sbs, with the host

@@ -63,6 +63,13 @@ struct LineArgs {
     // (whole image: 0, H, 0, H).  Row indices stay image rows; the volume pointers of a band are biased so
     // that row v_lo is the first allocated one.
     int v_begin, v_end, v_lo, v_hi;
+    // Row-band neighbours (peer-to-peer halo, fused into the producing pass): outputs on local rows
+    // < peer_lo_end are ALSO stored into the upper neighbour's volume, rows >= peer_hi_begin into the lower
+    // one's.  peer_out[side][view slot] is the neighbour's buffer (peer-mapped over NVLink, or another context
+    // of this process) biased so that THIS band's local row index addresses the neighbour's halo row.
+    // Null / 0 / INT_MAX: no neighbour on that side, or not a pass whose output is exchanged.
+    float4 *peer_out[2][2];
+    int peer_lo_end, peer_hi_begin;
 };
 
 // shared-memory bytes of one CTA
@@ -381,6 +388,7 @@ k_line(const LineArgs a)
     char *dstp = nullptr;
     if (MODE != LM_H_WTA)
         dstp = reinterpret_cast<char *>(a.out[vslot] + line_base4) + (long long)(t0 + 4 * team) * ostride;
+    const bool has_peer = MODE != LM_H_WTA && (a.peer_out[0][vslot] != nullptr || a.peer_out[1][vslot] != nullptr);
     for (int it = 0, g = team; it < niter; ++it, g += TEAMS, pS += 4 * TEAMS, dstp += 4 * TEAMS * ostride) {
         const bool active = g < ngroups;
         uint4 ws = make_uint4(0u, 0u, 0u, 0u), we = ws;
@@ -403,6 +411,19 @@ k_line(const LineArgs a)
 #pragma unroll
                     for (int i = 0; i < 3; ++i)
                         if (i < rem) *reinterpret_cast<float4 *>(dstp + i * ostride) = acc[i];
+                }
+                if (has_peer) {  // block-uniform: this launch feeds a neighbouring band's halo rows
+                    // (everything about the neighbours is fetched here, in the rare path, not kept in registers)
+                    const bool peer_up = a.peer_out[0][vslot] != nullptr, peer_dn = a.peer_out[1][vslot] != nullptr;
+                    // byte distance from this band's own output to the same element in the neighbour's buffer
+                    const long long d_up = reinterpret_cast<char *>(a.peer_out[0][vslot]) - reinterpret_cast<char *>(a.out[vslot]);
+                    const long long d_dn = reinterpret_cast<char *>(a.peer_out[1][vslot]) - reinterpret_cast<char *>(a.out[vslot]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = VERT ? (t0 + 4 * g + i) : ln;  // local image row of output i
+                        if (i < rem && r < a.peer_lo_end && peer_up) *reinterpret_cast<float4 *>(dstp + i * ostride + d_up) = acc[i];
+                        if (i < rem && r >= a.peer_hi_begin && peer_dn) *reinterpret_cast<float4 *>(dstp + i * ostride + d_dn) = acc[i];
+                    }
                 }
             }
         } else {
@@ -473,6 +494,27 @@ k_line(const LineArgs a)
             }
         }
     }
+}
+
+// Neighbour hand-shake of the row-band mode, on the stream, no host involvement: after a pass whose output
+// feeds the neighbours' halos, k_band_signal publishes everything this stream has written so far and bumps
+// an epoch word in the neighbour's memory; before the pass that reads the halos, k_band_wait spins on this
+// band's own epoch word until the neighbour has got that far.  (Bounded: a neighbour that never arrives sets
+// *status instead of hanging the GPU.)
+__global__ void k_band_signal(unsigned int *peer_flag, unsigned int epoch)
+{
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flag), "r"(epoch) : "memory");
+}
+__global__ void k_band_wait(const unsigned int *flag, unsigned int epoch, unsigned int *status)
+{
+    unsigned int v = 0;
+    for (long long spin = 0; spin < 4000000; ++spin) {  // ~4 s at 1 us per probe
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - epoch) >= 0) return;
+        __nanosleep(1000);
+    }
+    *status = 1u;
 }
 
 }  // namespace s2mv

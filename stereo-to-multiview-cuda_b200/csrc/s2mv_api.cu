@@ -219,6 +219,17 @@ struct s2mv_ctx {
     // row-band mode (s2mv_band.inl): this context is a sub-image of a taller frame
     bool band = false;
     int band_frame_rows = 0, band_ly0 = 0, band_o0 = 0, band_o1 = 0, band_vlo = 0, band_vhi = 0;
+    // peer-to-peer halos: the neighbours' volumes as seen from this process / device
+    struct BandPeer {
+        bool connected = false;
+        float *vol[2] = {};          // neighbour's volume A / B allocation bases (peer-mapped or same process)
+        unsigned int *flag = nullptr;  // the neighbour's epoch word that THIS band bumps
+        long long row_bias = 0;      // neighbour allocation row = local row + row_bias
+        size_t view_stride4 = 0;     // neighbour's float4 per view
+        void *ipc[3] = {};           // mappings to close (cudaIpcOpenMemHandle)
+    } band_peer[2];
+    unsigned int *band_flags = nullptr;  // [0] bumped by the upper neighbour, [1] by the lower, [2] status
+    unsigned int band_epoch = 0;
     // two-resolution mode (adcensus_stm_2): this context works at full resolution (no cost volumes), `lo` is a
     // whole context at the disparity resolution
     s2mv_ctx *lo = nullptr;
@@ -291,6 +302,12 @@ static int dev_alloc_t(s2mv_ctx *c, T **p, size_t count) { return dev_alloc(c, (
 static void free_arena(s2mv_ctx *c)
 {
     stream_release(c);
+    for (auto &pr : c->band_peer) {
+        for (void *m : pr.ipc)
+            if (m) cudaIpcCloseMemHandle(m);
+        pr = s2mv_ctx::BandPeer();
+    }
+    c->band_flags = nullptr;
     for (void *p : c->allocs) cudaFree(p);
     c->allocs.clear();
     c->arena_bytes = 0;
@@ -518,6 +535,11 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
         }
     }
     TRY(dev_alloc_t(c, &c->irv_count, 8));
+    if (band) {
+        TRY(dev_alloc_t(c, &c->band_flags, 4));
+        CU(cudaMemset(c->band_flags, 0, 4 * sizeof(unsigned int)));
+        c->band_epoch = 0;
+    }
     TRY(dev_alloc_t(c, &c->tmask, n));
     TRY(dev_alloc_t(c, &c->lutAd, 768));
     TRY(dev_alloc_t(c, &c->lutCen, 68));

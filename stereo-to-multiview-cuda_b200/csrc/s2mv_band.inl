@@ -102,8 +102,39 @@ extern "C" int s2mv_band_pass(s2mv_ctx *c, int pass, void *stream)
     LineArgs a;
     fill_largs(c, a, p.num_rows, p.num_cols, p.zero_disp, p.ad_coeff);
     for (int v = 0; v < 2; ++v) { a.arms[v] = c->arms[v]; a.wta_key[v] = c->wta_key[v]; a.disp[v] = c->disp[v]; }
+    const bool p2p = c->band_peer[0].connected || c->band_peer[1].connected;
+    a.peer_lo_end = 0;
+    a.peer_hi_begin = 0x7fffffff;
+    if (p2p && (pass == 2 || pass == 3)) {
+        // the halo rows this pass reads are written by the neighbours' previous pass: wait for their epoch
+        for (int side = 0; side < 2; ++side)
+            if (c->band_peer[side].connected) {
+                k_band_wait<<<1, 1, 0, st>>>(c->band_flags + side, c->band_epoch, c->band_flags + 2);
+                KCHECK();
+            }
+    }
+    if (p2p && (pass == 1 || pass == 2)) {
+        // this pass's rows next to a band edge also go straight into the neighbour's halo rows
+        const int usd = p.usd, buf = pass == 1 ? 0 : 1;
+        for (int side = 0; side < 2; ++side) {
+            const s2mv_ctx::BandPeer &pr = c->band_peer[side];
+            if (!pr.connected) continue;
+            for (int v = 0; v < 2; ++v)
+                a.peer_out[side][v] = reinterpret_cast<float4 *>(pr.vol[buf]) + (size_t)v * pr.view_stride4 +
+                                      pr.row_bias * (long long)row4;
+            if (side == 0) a.peer_lo_end = rr.own0 + usd; else a.peer_hi_begin = rr.own1 - usd;
+        }
+    }
     TRY(launch_pass(c, a, pass, reinterpret_cast<float4 *>(c->vol[0]), reinterpret_cast<float4 *>(c->vol[1]), view_stride4,
                     2, true, true, rr, st));
+    if (p2p && (pass == 1 || pass == 2)) {
+        c->band_epoch += 1;
+        for (int side = 0; side < 2; ++side)
+            if (c->band_peer[side].connected) {
+                k_band_signal<<<1, 1, 0, st>>>(c->band_peer[side].flag, c->band_epoch);
+                KCHECK();
+            }
+    }
     if (pass == 4 && c->plan.nchunks > 1) {
         k_wta_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->wta_key[0], c->disp[0], p.zero_disp, n);
         k_wta_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->wta_key[1], c->disp[1], p.zero_disp, n);
@@ -162,5 +193,106 @@ extern "C" int s2mv_band_finish(s2mv_ctx *c, float *d_disp_l_band, float *d_disp
     if (d_disp_l_band) CU(cudaMemcpyAsync(d_disp_l_band, c->dispF[0] + off, own * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (d_disp_r_band) CU(cudaMemcpyAsync(d_disp_r_band, c->dispF[1] + off, own * W * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (d_interlaced_band) CU(cudaMemcpyAsync(d_interlaced_band, c->interlaced + off * 3, own * W * 3, cudaMemcpyDeviceToDevice, st));
+    return S2MV_OK;
+}
+
+// ---- peer-to-peer halos -------------------------------------------------------------------------
+// With the neighbours connected, passes 1 and 2 store the rows next to a band edge straight into the
+// neighbour's halo rows (peer-mapped memory: NVLink stores issued by the producing kernel, tile by tile)
+// and the caller exchanges nothing: s2mv_band_pass orders the bands with an epoch word per neighbour
+// (k_band_signal / k_band_wait on the stream).  Every band of a frame must then run the same pass
+// sequence, and all of a frame's passes 1 (and 2) must be enqueued before any band waits when several
+// bands share one stream.
+static int band_attach(s2mv_ctx *c, int side, float *volA, float *volB, unsigned int *peer_flags, int peer_ly0,
+                       int peer_vlo, int peer_vrows)
+{
+    s2mv_ctx::BandPeer &pr = c->band_peer[side];
+    pr.vol[0] = volA;
+    pr.vol[1] = volB;
+    pr.flag = peer_flags + (1 - side);  // I am the neighbour's lower (side 0: I attach my upper) / upper neighbour
+    pr.row_bias = (long long)c->band_ly0 - peer_ly0 - peer_vlo;
+    pr.view_stride4 = (size_t)peer_vrows * c->prm.num_cols * c->plan.LPtot;
+    pr.connected = true;
+    return S2MV_OK;
+}
+
+// same process: `peer` is the band context above (side 0) or below (side 1) this one
+extern "C" int s2mv_band_connect(s2mv_ctx *c, int side, s2mv_ctx *peer)
+{
+    TRY(band_check(c));
+    TRY(band_check(peer));
+    if (side < 0 || side > 1) return fail(S2MV_ERR_BAD_PARAM, "side must be 0 (upper neighbour) or 1 (lower)");
+    if (peer->prm.num_cols != c->prm.num_cols || peer->plan.LPtot != c->plan.LPtot || peer->band_frame_rows != c->band_frame_rows)
+        return fail(S2MV_ERR_BAD_PARAM, "neighbour bands must belong to the same frame");
+    const int my_edge = c->band_ly0 + (side == 0 ? c->band_o0 : c->band_o1);
+    const int peer_edge = peer->band_ly0 + (side == 0 ? peer->band_o1 : peer->band_o0);
+    if (my_edge != peer_edge) return fail(S2MV_ERR_BAD_PARAM, "bands are not adjacent (rows %d vs %d)", my_edge, peer_edge);
+    if (peer->device != c->device) {
+        CU(cudaSetDevice(c->device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(S2MV_ERR_CUDA, "no peer access %d -> %d: %s", c->device, peer->device, cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    return band_attach(c, side, peer->vol[0], peer->vol[1], peer->band_flags, peer->band_ly0, peer->band_vlo,
+                       peer->band_vhi - peer->band_vlo);
+}
+
+// other process (one process per GPU): what a neighbour needs to map this band's volumes
+extern "C" int s2mv_band_ipc_export(s2mv_ctx *c, s2mv_band_ipc *out)
+{
+    TRY(band_check(c));
+    if (!out) return fail(S2MV_ERR_BAD_PARAM, "null argument");
+    CU(cudaSetDevice(c->device));
+    memset(out, 0, sizeof(*out));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    void *ptrs[3] = {c->vol[0], c->vol[1], c->band_flags};
+    for (int i = 0; i < 3; ++i) {
+        CU(cudaIpcGetMemHandle(&h, ptrs[i]));
+        memcpy(out->mem[i], &h, 64);
+    }
+    out->frame_y0 = c->band_ly0 + c->band_o0;
+    out->frame_y1 = c->band_ly0 + c->band_o1;
+    out->local_y0 = c->band_ly0;
+    out->vlo = c->band_vlo;
+    out->vrows = c->band_vhi - c->band_vlo;
+    out->num_cols = c->prm.num_cols;
+    out->lptot = c->plan.LPtot;
+    out->frame_rows = c->band_frame_rows;
+    out->device = c->device;
+    return S2MV_OK;
+}
+
+extern "C" int s2mv_band_ipc_connect(s2mv_ctx *c, int side, const s2mv_band_ipc *peer)
+{
+    TRY(band_check(c));
+    if (!peer || side < 0 || side > 1) return fail(S2MV_ERR_BAD_PARAM, "bad argument");
+    if (peer->num_cols != c->prm.num_cols || peer->lptot != c->plan.LPtot || peer->frame_rows != c->band_frame_rows)
+        return fail(S2MV_ERR_BAD_PARAM, "neighbour bands must belong to the same frame");
+    const int my_edge = c->band_ly0 + (side == 0 ? c->band_o0 : c->band_o1);
+    const int peer_edge = side == 0 ? peer->frame_y1 : peer->frame_y0;
+    if (my_edge != peer_edge) return fail(S2MV_ERR_BAD_PARAM, "bands are not adjacent (rows %d vs %d)", my_edge, peer_edge);
+    CU(cudaSetDevice(c->device));
+    s2mv_ctx::BandPeer &pr = c->band_peer[side];
+    void *m[3] = {};
+    for (int i = 0; i < 3; ++i) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, peer->mem[i], 64);
+        CU(cudaIpcOpenMemHandle(&m[i], h, cudaIpcMemLazyEnablePeerAccess));
+        pr.ipc[i] = m[i];
+    }
+    return band_attach(c, side, (float *)m[0], (float *)m[1], (unsigned int *)m[2], peer->local_y0, peer->vlo, peer->vrows);
+}
+
+// 0 when every wait of this band met its neighbour; synchronises the context's stream
+extern "C" int s2mv_band_status(s2mv_ctx *c, void *stream)
+{
+    TRY(band_check(c));
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    unsigned int status = 0;
+    CU(cudaMemcpyAsync(&status, c->band_flags + 2, sizeof(status), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (status) return fail(S2MV_ERR_CUDA, "a neighbouring band never reached the pass this band waited for");
     return S2MV_OK;
 }

@@ -71,6 +71,13 @@ def _as_tensor(ptr, shape, typestr, device):
     return torch.as_tensor(_DevMem(ptr, shape, typestr), device=torch.device("cuda", device))
 
 
+class BandIpc(C.Structure):
+    """s2mv_band_ipc (include/s2mv.h): what a neighbouring process needs to map a band's volumes."""
+    _fields_ = [("mem", (C.c_ubyte * 64) * 3), ("frame_y0", C.c_int), ("frame_y1", C.c_int), ("local_y0", C.c_int),
+                ("vlo", C.c_int), ("vrows", C.c_int), ("num_cols", C.c_int), ("lptot", C.c_int), ("frame_rows", C.c_int),
+                ("device", C.c_int)]
+
+
 class RowBand:
     """One band context: thin mirror of the s2mv_band_* C ABI with torch views of its halo runs."""
 
@@ -116,6 +123,24 @@ class RowBand:
         _check(self.pipe._L.s2mv_band_disp(self.pipe._ctx, view, C.byref(ptr)))
         return _as_tensor(ptr.value, (self.local_rows, self.W), "<f4", self.device)
 
+    # peer-to-peer halos (side 0 = the band above, 1 = the band below)
+    def connect(self, side, other):
+        """Same process: `other` is the neighbouring RowBand."""
+        _check(self.pipe._L.s2mv_band_connect(self.pipe._ctx, int(side), other.pipe._ctx))
+
+    def ipc_export(self):
+        """bytes of this band's s2mv_band_ipc, to be carried to the neighbouring processes."""
+        b = BandIpc()
+        _check(self.pipe._L.s2mv_band_ipc_export(self.pipe._ctx, C.byref(b)))
+        return bytes(b)
+
+    def ipc_connect(self, side, blob):
+        b = BandIpc.from_buffer_copy(blob)
+        _check(self.pipe._L.s2mv_band_ipc_connect(self.pipe._ctx, int(side), C.byref(b)))
+
+    def status(self, stream=None):
+        _check(self.pipe._L.s2mv_band_status(self.pipe._ctx, self._st(stream)))
+
     def finish(self, d_disp_l, d_disp_r, d_interlaced, stream=None):
         """torch tensors (own_rows x W [x3]) or None."""
         g = lambda t: C.c_void_p(0 if t is None else t.data_ptr())  # noqa: E731
@@ -136,6 +161,10 @@ def _declare(L):
     L.s2mv_band_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.s2mv_configure_band.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.s2mv_band_info.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    L.s2mv_band_connect.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.s2mv_band_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+    L.s2mv_band_ipc_connect.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.s2mv_band_status.argtypes = [C.c_void_p, C.c_void_p]
 
 
 # ------------------------------------------------------------- one process
@@ -143,7 +172,9 @@ class LocalBands:
     """All bands of a frame in this process; `devices` gives each band's GPU (repeat an index to run
     several bands on one GPU).  process() returns the assembled (disp_l, disp_r, interlaced) tensors."""
 
-    def __init__(self, devices, apron=0, **frame_params):
+    def __init__(self, devices, apron=0, p2p=True, **frame_params):
+        """p2p: the producing passes store the halo rows straight into the neighbouring band's volume (peer stores,
+        epoch words on the stream); False: halos are copied between the passes (Tensor.copy_)."""
         import torch
         from . import default_params
         self.torch = torch
@@ -151,6 +182,13 @@ class LocalBands:
         self.H, self.W = p.num_rows, p.num_cols
         self.bands = row_bands(self.H, len(devices), min_rows=p.usd)
         self.ctx = [RowBand(d, y0, y1, apron, **frame_params) for d, (y0, y1) in zip(devices, self.bands)]
+        self.p2p = p2p
+        if p2p:
+            for b, c in enumerate(self.ctx):
+                if b > 0:
+                    c.connect(0, self.ctx[b - 1])
+                if b < len(self.ctx) - 1:
+                    c.connect(1, self.ctx[b + 1])
 
     def close(self):
         for c in self.ctx:
@@ -178,13 +216,15 @@ class LocalBands:
                 st = torch.cuda.current_stream(c.device).cuda_stream
                 c.prepare(d_sbs_by_device[c.device].data_ptr(), num_cols_sbs, st)
                 c.run_pass(1, st)
-        self._sync()
-        self._exchange(1)
+        if not self.p2p:
+            self._sync()
+            self._exchange(1)
         for c in self.ctx:
             with torch.cuda.device(c.device):
                 c.run_pass(2, torch.cuda.current_stream(c.device).cuda_stream)
-        self._sync()
-        self._exchange(2)
+        if not self.p2p:
+            self._sync()
+            self._exchange(2)
         for c in self.ctx:
             with torch.cuda.device(c.device):
                 st = torch.cuda.current_stream(c.device).cuda_stream
@@ -251,11 +291,14 @@ def allgather_rows_dist(own, bands, dist, torch):
 class DistBand:
     """This rank's band of a frame split over the process group (one process per GPU)."""
 
-    def __init__(self, device, rank, world, apron=0, **frame_params):
+    def __init__(self, device, rank, world, apron=0, transport="p2p", **frame_params):
+        """transport "p2p": neighbours' volumes mapped through CUDA IPC, halo rows stored over NVLink by the
+        producing kernels; "nccl": halos sent with torch.distributed point-to-point ops between the passes."""
         import torch
         import torch.distributed as dist
         from . import default_params
         self.torch, self.dist = torch, dist
+        self.transport = transport if world > 1 else "none"
         p = default_params(**frame_params)
         self.H, self.W = p.num_rows, p.num_cols
         self.rank, self.world = rank, world
@@ -266,6 +309,14 @@ class DistBand:
         self.out_l = torch.empty((c.own_rows, self.W), dtype=torch.float32, device=f"cuda:{device}")
         self.out_r = torch.empty_like(self.out_l)
         self.out_i = torch.empty((c.own_rows, self.W, 3), dtype=torch.uint8, device=f"cuda:{device}")
+        if self.transport == "p2p":
+            blobs = [None] * world
+            dist.all_gather_object(blobs, c.ipc_export())
+            if rank > 0:
+                c.ipc_connect(0, blobs[rank - 1])
+            if rank < world - 1:
+                c.ipc_connect(1, blobs[rank + 1])
+            dist.barrier()
 
     def close(self):
         self.ctx.close()
@@ -289,12 +340,12 @@ class DistBand:
         mark("prepare")
         c.run_pass(1, st)
         mark("pass1")
-        if self.world > 1:
+        if self.transport == "nccl":
             exchange_halos_dist(lambda side, recv: [c.halo(1, v, side, recv) for v in (0, 1)], self.rank, self.world, dist)
         mark("halo1")
         c.run_pass(2, st)
         mark("pass2")
-        if self.world > 1:
+        if self.transport == "nccl":
             exchange_halos_dist(lambda side, recv: [c.halo(2, v, side, recv) for v in (0, 1)], self.rank, self.world, dist)
         mark("halo2")
         c.run_pass(3, st)

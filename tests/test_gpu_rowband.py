@@ -11,15 +11,19 @@ pytestmark = pytest.mark.gpu
 ALGO = {k: DEFAULTS[k] for k in ("ad_coeff", "census_coeff", "ucd", "lcd", "usd", "lsd", "thresh_s", "thresh_h")}
 
 
-@pytest.mark.parametrize("H,W,D,zd,nbands", [(400, 320, 32, 16, 3), (300, 336, 160, 70, 2), (531, 200, 64, 32, 4)])
-def test_row_bands_equal_whole_frame(s2mv, H, W, D, zd, nbands):
+@pytest.mark.parametrize("p2p", [True, False])
+@pytest.mark.parametrize("H,W,D,zd,nbands", [(400, 320, 32, 16, 3), (300, 336, 160, 70, 2), (531, 200, 64, 32, 4),
+                                             (120, 192, 128, 60, 5)])
+def test_row_bands_equal_whole_frame(s2mv, H, W, D, zd, nbands, p2p):
     import torch
     from s2mv_b200_pkg import rowband, synth
     sbs = synth.make_sbs(H, W, 4000 + H)
     params = dict(num_rows=H, num_cols=W, num_disp=D, zero_disp=zd, num_views=8, angle=18, **ALGO)
     with s2mv.Pipeline(0, **params) as p:
         wl, wr, wo = p.adcensus_stm(sbs)
-    lb = rowband.LocalBands([0] * nbands, **params)
+    # p2p: halo rows stored by the producing pass straight into the neighbouring band's volume (here: another
+    # context on the same GPU), epoch words on the stream; otherwise copied between the passes
+    lb = rowband.LocalBands([0] * nbands, p2p=p2p, **params)
     try:
         assert [c.own_rows for c in lb.ctx] == [y1 - y0 for y0, y1 in lb.bands]
         d_sbs = torch.from_numpy(sbs).cuda()
@@ -27,6 +31,11 @@ def test_row_bands_equal_whole_frame(s2mv, H, W, D, zd, nbands):
         assert np.array_equal(dl.cpu().numpy(), wl)
         assert np.array_equal(dr.cpu().numpy(), wr)
         assert np.array_equal(out.cpu().numpy(), wo)
+        if p2p:
+            for c in lb.ctx:
+                c.status()                                       # every wait met its neighbour
+            dl2, dr2, out2 = lb.process({0: d_sbs}, 2 * W)      # a second frame through the same epoch words
+            assert np.array_equal(dl2.cpu().numpy(), wl) and np.array_equal(out2.cpu().numpy(), wo)
         # a band context refuses the whole-frame entry points
         with pytest.raises(s2mv.S2mvError):
             lb.ctx[0].pipe.process_device(d_sbs.data_ptr(), 2 * W)

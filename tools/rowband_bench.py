@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--check", action="store_true", help="compare with the single-context frame on rank 0")
     ap.add_argument("--baseline", action="store_true", help="also time the single-context frame on rank 0")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="halo rows: peer stores from the producing kernels over CUDA IPC mappings, or NCCL send/recv")
     ap.add_argument("--sha", action="store_true", help="print SHA-256 of the assembled outputs (to compare runs whose "
                                                        "single-context frame does not fit next to a band)")
     ap.add_argument("--single", action="store_true", help="N = 1 only: time the ordinary single-context frame "
@@ -77,7 +79,7 @@ def main():
         print(json.dumps(res), flush=True)
         return 0
 
-    band = rowband.DistBand(local_rank, rank, world, **params)
+    band = rowband.DistBand(local_rank, rank, world, transport=args.transport, **params)
     for _ in range(args.warmup):
         band.process(d_sbs, 2 * W)
     torch.cuda.synchronize()
@@ -108,7 +110,10 @@ def main():
                (D + 127) // 128 * 128 if D > 128 else 1 << (max(D, 4) - 1).bit_length()),
            "phase_ms_max_over_ranks": {k: max(p[k] for p in allph) for k in phases},
            "phase_ms_rank0": phases,
-           "arena_gb_per_gpu": arena / 1e9, "transport": "torch.distributed NCCL send/recv + all_gather (disparity rows)"}
+           "arena_gb_per_gpu": arena / 1e9, "transport": {"p2p": "halo rows stored by the producing kernels into CUDA-IPC-mapped neighbour volumes (NVLink), epoch words "
+                                "on the stream; NCCL all_gather of the disparity rows",
+                         "nccl": "torch.distributed NCCL send/recv of the halo rows + all_gather of the disparity rows",
+                         "none": "one band"}[band.transport]}
 
     if args.sha:
         import hashlib
