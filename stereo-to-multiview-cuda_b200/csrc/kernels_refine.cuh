@@ -204,14 +204,19 @@ k_irv_vote(const IrvArgs a)
 // adds: one coalesced 128-byte load per support row instead of a row of scattered loads and shared-memory
 // atomics.  Same histogram, same count, same first-maximum rule as k_irv_vote.
 constexpr int kHsegThreads = 128;
+#ifndef S2MV_IRV_BATCH
+#define S2MV_IRV_BATCH 4
+#endif
 
+template <int NW>  // 128-bin words per pixel: nbp = 128 * NW
 __global__ void __launch_bounds__(kHsegThreads)
 k_irv_hseg(const IrvArgs a)
 {
     extern __shared__ __align__(16) uint8_t hs[];  // [kHsegThreads][nbp + 4]: the pad staggers the banks
     const int v = blockIdx.y;
     if (*a.count[v] < a.dense_min) return;
-    const int W = a.W, nbp = a.nbp, pitch = nbp + 4;
+    constexpr int nbp = 128 * NW, pitch = nbp + 4;
+    const int W = a.W;
     const int tiles_x = (W + kHsegThreads - 1) / kHsegThreads, ntiles = tiles_x * a.H;
     const float *__restrict__ disp = a.disp[v];
     const uint8_t *__restrict__ outl = a.outliers[v];
@@ -240,11 +245,13 @@ k_irv_hseg(const IrvArgs a)
         __syncthreads();
         // out: one pixel's nbp bytes per warp step, 128 bytes per store instruction, pointers walked by increments
         const int npix = min(kHsegThreads, W - bx);
-        const int wpp = nbp / 4, wps = pitch / 4;  // 32-bit words per pixel: global / shared
+        constexpr int wpp = nbp / 4, wps = pitch / 4;  // 32-bit words per pixel: global / shared
         uint32_t *__restrict__ d = reinterpret_cast<uint32_t *>(hseg + ((size_t)gy * W + bx) * nbp) + (size_t)warp * wpp + lane;
         const uint32_t *sp = hw + warp * wps + lane;
-        for (int i = warp; i < npix; i += kHsegThreads / 32, d += (kHsegThreads / 32) * wpp, sp += (kHsegThreads / 32) * wps)
-            for (int w = 0; w < wpp; w += 32) d[w] = sp[w];
+        for (int i = warp; i < npix; i += kHsegThreads / 32, d += (kHsegThreads / 32) * wpp, sp += (kHsegThreads / 32) * wps) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) d[32 * w] = sp[32 * w];
+        }
         __syncthreads();
     }
 }
@@ -262,10 +269,10 @@ k_irv_vote_dense(const IrvArgs a)
     const uint32_t *__restrict__ hseg = reinterpret_cast<const uint32_t *>(a.hseg[v]);
     const int W = a.W;
     constexpr int WPP = 32 * NW;  // 32-bit words per pixel
-    // Entries are handed out in list (= raster) order, 16 per ticket: the warps in flight then work on
+    // Entries are handed out in list (= raster) order, a few per ticket (4 measured best): the warps in flight then work on
     // neighbouring image rows, whose span histograms they share through L2 (with a fixed stride per warp the
     // uneven cost per entry lets the warps drift apart)
-    constexpr int kBatch = 16;
+    constexpr int kBatch = S2MV_IRV_BATCH;
     for (int e = 0, e_end = 0;; ++e) {
         if (e == e_end) {
             if (lane == 0) e = atomicAdd(a.ticket[v], kBatch);

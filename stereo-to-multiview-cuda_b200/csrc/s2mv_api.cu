@@ -405,7 +405,10 @@ static int set_kernel_attrs()
     TRY(set_smem(k_gauss_dilate4<10>, 64 * 1024));
     TRY(set_smem(k_gauss_dilate, 160 * 1024));
     TRY(set_smem(k_irv_vote, 64 * 1024));
-    TRY(set_smem(k_irv_hseg, 100 * 1024));
+    TRY(set_smem(k_irv_hseg<1>, 100 * 1024));
+    TRY(set_smem(k_irv_hseg<2>, 100 * 1024));
+    TRY(set_smem(k_irv_hseg<3>, 100 * 1024));
+    TRY(set_smem(k_irv_hseg<4>, 100 * 1024));
     TRY(set_smem(k_arms_tile, 160 * 1024));
     return S2MV_OK;
 }
@@ -854,7 +857,16 @@ static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2],
     for (int v = 0; v < nviews; ++v) a.hseg[v] = dense_ok ? c->irv_hseg[v] : nullptr;
     for (int it = 0; it < iterations; ++it) {
         if (dense_ok) {
-            k_irv_hseg<<<dim3(c->sm_count * 8, nviews), kHsegThreads, (size_t)kHsegThreads * (a.nbp + 4), st>>>(a);
+            {
+                const dim3 gh(c->sm_count * 8, nviews);
+                const size_t sh = (size_t)kHsegThreads * (a.nbp + 4);
+                switch (a.nbp / 128) {
+                    case 1: k_irv_hseg<1><<<gh, kHsegThreads, sh, st>>>(a); break;
+                    case 2: k_irv_hseg<2><<<gh, kHsegThreads, sh, st>>>(a); break;
+                    case 3: k_irv_hseg<3><<<gh, kHsegThreads, sh, st>>>(a); break;
+                    default: k_irv_hseg<4><<<gh, kHsegThreads, sh, st>>>(a); break;
+                }
+            }
             KCHECK();
             const dim3 gd(c->sm_count * 8, nviews);
             switch (a.nbp / 128) {
