@@ -66,3 +66,25 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.lower(), os.path.join(dirpath, f)
+
+
+def test_headers_compile_and_struct_sizes_match_ctypes(s2mv, tmp_path):
+    """include/s2mv.h is plain C (any FFI can bind it), include/s2mv_compat.h is the reference's C++ surface; the
+    ctypes mirrors of the two structs have the C compiler's size and field offsets."""
+    import subprocess
+    from s2mv_b200_pkg import rowband
+    inc = os.path.join(ROOT, "include")
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "s2mv.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(s2mv_params), offsetof(s2mv_params, thresh_h), '
+                   'offsetof(s2mv_params, mask_blur_sigma), sizeof(s2mv_band_ipc), offsetof(s2mv_band_ipc, frame_y0), '
+                   'offsetof(s2mv_band_ipc, device)); return 0; }\n')
+    exe = tmp_path / "t"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
+    P, B = s2mv.Params, rowband.BandIpc
+    assert got == [ctypes.sizeof(P), P.thresh_h.offset, P.mask_blur_sigma.offset, ctypes.sizeof(B), B.frame_y0.offset,
+                   B.device.offset]
+    cxx = tmp_path / "t.cpp"
+    cxx.write_text('#include "s2mv_compat.h"\n#include "s2mv.h"\nint main() { return 0; }\n')
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-I", inc, str(cxx)])
