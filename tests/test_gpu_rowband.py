@@ -54,3 +54,30 @@ def test_band_configuration_errors(s2mv):
         rowband.RowBand(0, 0, 100, apron=20, **params)           # apron below the vertical reach
     with pytest.raises(s2mv.S2mvError):
         rowband.RowBand(0, 0, 100, num_rows_out=100, **params)   # rescaling output
+
+
+@pytest.mark.parametrize("p2p", [True, False])
+def test_bands_on_two_devices_in_one_process(s2mv, p2p):
+    """Needs two GPUs (skipped otherwise): the bands live on different devices of one process, the halo rows
+    cross NVLink as peer stores from the producing kernels (p2p) or as device-to-device copies."""
+    import torch
+    from s2mv_b200_pkg import rowband, synth
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    H, W, D, zd = 420, 352, 96, 40
+    sbs = synth.make_sbs(H, W, 515)
+    params = dict(num_rows=H, num_cols=W, num_disp=D, zero_disp=zd, num_views=8, angle=18, **ALGO)
+    with s2mv.Pipeline(0, **params) as p:
+        wl, wr, wo = p.adcensus_stm(sbs)
+    lb = rowband.LocalBands([0, 1, 0], p2p=p2p, **params)
+    try:
+        frames = {d: torch.from_numpy(sbs).to(f"cuda:{d}") for d in (0, 1)}
+        for _ in range(2):
+            dl, dr, out = lb.process(frames, 2 * W)
+            assert np.array_equal(dl.cpu().numpy(), wl) and np.array_equal(dr.cpu().numpy(), wr)
+            assert np.array_equal(out.cpu().numpy(), wo)
+        if p2p:
+            for c in lb.ctx:
+                c.status()
+    finally:
+        lb.close()
