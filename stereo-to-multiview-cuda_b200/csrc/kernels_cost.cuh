@@ -11,15 +11,12 @@
 // Sums are the reference's sequential ascending fp32 adds from 0
 // (d_ca_cross_sum.cu:282-290): bit-exact, never reassociated or contracted.
 //
-// Kernels:
-//   k_hpass<FROM_CI,...>  one image row segment per CTA.  FROM_CI builds the
-//       ADCensus cost tile in shared memory (never written to HBM) and sums it
-//       horizontally (pass 1); otherwise the tile is loaded from the volume
-//       (pass 4), optionally reduced straight to the WTA disparity so the final
-//       volume is never written either.
-//   k_vpass               one (pixel, float4 lane) column per thread, streaming
-//       down a row band through a thread-private shared-memory ring fed by
-//       cp.async: no block barrier anywhere, each input row is read once.
+// Kernels here: what the stage entry points need besides the line kernel of kernels_line.cuh (which
+// does the frame path's four passes):
+//   k_hpass<MODE,...>     one image row segment per CTA: builds the AD / census / ADCensus cost tile in shared
+//                         memory and stores it (s2mv_ci_ad, s2mv_ci_census, s2mv_ci_adcensus)
+//   k_wta_finish          D > 128: (cost, d) keys of the chunked WTA -> disparities
+//   k_planes_to_vol / k_vol_to_planes / k_wta_planes   the reference's plane tables <-> the volume layout
 #pragma once
 #include <float.h>
 
@@ -28,8 +25,6 @@
 namespace s2mv {
 
 constexpr int kHThreads = 256;
-constexpr int kVThreads = 128;
-constexpr int kVPrefetch = 6;  // rows in flight ahead of the vertical window
 
 struct HArgs {
     // cost-initialisation inputs (FROM_CI)
@@ -229,71 +224,6 @@ __global__ void k_wta_finish(const unsigned long long *__restrict__ key, float *
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     disp[i] = (float)(int)(uint32_t)(key[i] & 0xffffffffull) - (float)zd;
-}
-
-struct VArgs {
-    const float4 *in[2];
-    float4 *out[2];
-    const uint32_t *arms[2];
-    int H, W, LPtot, usd, rows_per_band;
-};
-
-// Vertical pass (ca_cross_vhsum_kernel_2 on transposed data in the reference,
-// d_ca_cross_sum.cu:148-198; here no transpose exists).
-__global__ void __launch_bounds__(kVThreads)
-k_vpass(const VArgs a)
-{
-    extern __shared__ __align__(16) float4 ring[];  // [R][kVThreads], thread-private columns
-    const int tid = threadIdx.x;
-    const size_t rowstride = (size_t)a.W * a.LPtot;
-    const size_t col = (size_t)blockIdx.x * kVThreads + tid;
-    if (col >= rowstride) return;  // no barriers below: safe to leave
-    const int x = (int)(col / a.LPtot);
-    const int vslot = blockIdx.z;
-    const float4 *__restrict__ in = a.in[vslot] + col;
-    float4 *__restrict__ out = a.out[vslot] + col;
-    const uint32_t *__restrict__ arms = a.arms[vslot] + x;
-    const int H = a.H, usd = a.usd, R = 2 * usd + kVPrefetch;
-    const int y0 = blockIdx.y * a.rows_per_band, y1 = min(H, y0 + a.rows_per_band);
-    float4 *my = ring + tid;
-
-    // prologue: rows [y0-usd, y0+usd-1+PF) -> slots (row mod R)
-    int r = max(0, y0 - usd);
-    int slot = r % R;
-    const int pre_end = min(H, y0 + usd - 1 + kVPrefetch);
-    for (; r < pre_end; ++r) {
-        cp_async16(my + (size_t)slot * kVThreads, in + (size_t)r * rowstride);
-        slot = (slot + 1 == R) ? 0 : slot + 1;
-    }
-    cp_async_commit();
-    cp_async_wait<0>();  // the steady-state wait below only covers rows fetched inside the loop
-    // `r`/`slot` now name the next row to fetch (y + usd - 1 + PF at iteration y = y0 ... unless clipped)
-    r = y0 + usd - 1 + kVPrefetch;
-    slot = r % R;
-    int sy = y0 % R;  // slot of row y
-    uint32_t ar = arms[(size_t)y0 * a.W];
-    for (int y = y0; y < y1; ++y) {
-        if (r < H) cp_async16(my + (size_t)slot * kVThreads, in + (size_t)r * rowstride);
-        cp_async_commit();
-        ++r;
-        slot = (slot + 1 == R) ? 0 : slot + 1;
-        const uint32_t ar_next = (y + 1 < y1) ? arms[(size_t)(y + 1) * a.W] : 0u;
-        cp_async_wait<kVPrefetch>();  // everything up to row y+usd-1 has landed
-
-        const int U = arm_up(ar), n = U + arm_down(ar);
-        int s = sy - U;
-        if (s < 0) s += R;
-        const int n1 = min(n, R - s);
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 *p = my + (size_t)s * kVThreads;
-        for (int k = 0; k < n1; ++k) acc4(acc, p[(size_t)k * kVThreads]);  // rows [y-U, ...)
-        for (int k = 0; k < n - n1; ++k) acc4(acc, my[(size_t)k * kVThreads]);  // ... wrapped part
-        out[(size_t)y * rowstride] = acc;
-
-        ar = ar_next;
-        sy = (sy + 1 == R) ? 0 : sy + 1;
-    }
-    cp_async_wait<0>();
 }
 
 // Stage-API layout converters: D contiguous planes <-> [pixel][Dp] volume.

@@ -131,45 +131,8 @@ __device__ __forceinline__ int max_abs_diff3(uint32_t a, uint32_t b)
     return max(max((int)(d & 0xff), (int)((d >> 8) & 0xff)), (int)((d >> 16) & 0xff));
 }
 
-__device__ __forceinline__ int arm_walk(const uint32_t *__restrict__ pix, int x, int y, int dx, int dy,
-                                        uint32_t anchor, float ucd, float lcd, int usd, int lsd, int H, int W)
-{
-    uint32_t prev = anchor;
-    int arm = 0;
-    for (int s = 1; s <= usd; ++s) {
-        int cx = x + dx * s, cy = y + dy * s;
-        if (cx < 0 || cx > W - 1 || cy < 0 || cy > H - 1) break;
-        arm = s;
-        uint32_t c = __ldg(pix + (size_t)cy * W + cx);
-        float ac = (float)max_abs_diff3(c, anchor), cp = (float)max_abs_diff3(c, prev);
-        if (s > lsd) {
-            if (ac > ucd) break;
-        } else {
-            if (ac > lcd || cp > lcd) break;
-        }
-        prev = c;
-    }
-    return arm;
-}
-
-__global__ void __launch_bounds__(256)
-k_arms(const uint32_t *__restrict__ pix, uint32_t *__restrict__ arms, float ucd, float lcd, int usd, int lsd,
-       int H, int W)
-{
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y;
-    if (x >= W) return;
-    uint32_t a = pix[(size_t)y * W + x];
-    int u = arm_walk(pix, x, y, 0, -1, a, ucd, lcd, usd, lsd, H, W);
-    int d = arm_walk(pix, x, y, 0, +1, a, ucd, lcd, usd, lsd, H, W);
-    int l = arm_walk(pix, x, y, -1, 0, a, ucd, lcd, usd, lsd, H, W);
-    int r = arm_walk(pix, x, y, +1, 0, a, ucd, lcd, usd, lsd, H, W);
-    arms[(size_t)y * W + x] = (uint32_t)u | ((uint32_t)d << 8) | ((uint32_t)l << 16) | ((uint32_t)r << 24);
-}
-
-// Same arms, both views in one launch, pixels staged in shared memory: the walk
-// is a chain of up to 4*usd dependent loads; out of L2 each step costs ~600
-// cycles, out of shared memory ~30.
+// Both views in one launch, pixels staged in shared memory: the walk is a chain of up to 4*usd dependent
+// loads; out of L2 each step costs ~600 cycles, out of shared memory ~30.
 constexpr int kArmW = 64, kArmH = 16;
 __device__ __forceinline__ int arm_walk_tile(const uint32_t *__restrict__ t, int pitch, int x, int y, int dx, int dy,
                                              uint32_t anchor, float ucd, float lcd, int usd, int lsd, int H, int W)
