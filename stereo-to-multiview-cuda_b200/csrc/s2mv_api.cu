@@ -271,6 +271,8 @@ struct s2mv_ctx {
     float *h_disp[2] = {};
     size_t h_sbs_bytes = 0;
     // timing
+    cudaEvent_t ev_refined = nullptr;   // disparities final (before DIBR): the synchronous call starts their D2H here
+    cudaStream_t st_aux = nullptr;      // second copy stream of the synchronous host call
     cudaEvent_t ev[5] = {};
     cudaEvent_t kev[5] = {};  // around the four cost-volume kernels
     int launches = 0;
@@ -345,6 +347,8 @@ extern "C" int s2mv_create(s2mv_ctx **out, int device)
         return fail(S2MV_ERR_CUDA, "cudaStreamCreate failed");
     }
     for (int i = 0; i < 5; ++i) cudaEventCreate(&c->ev[i]);
+    cudaEventCreateWithFlags(&c->ev_refined, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&c->st_aux, cudaStreamNonBlocking);
     for (int i = 0; i < 5; ++i) cudaEventCreate(&c->kev[i]);
     *out = c;
     return S2MV_OK;
@@ -361,6 +365,8 @@ extern "C" void s2mv_destroy(s2mv_ctx *c)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
         if (c->kev[i]) cudaEventDestroy(c->kev[i]);
     }
+    if (c->ev_refined) cudaEventDestroy(c->ev_refined);
+    if (c->st_aux) cudaStreamDestroy(c->st_aux);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -988,6 +994,7 @@ static int run_refine_dibr(s2mv_ctx *c, float *d_disp_l, float *d_disp_r, uint8_
 {
     float *fl = d_disp_l ? d_disp_l : c->dispF[0], *fr = d_disp_r ? d_disp_r : c->dispF[1];
     TRY(run_refine(c, fl, fr, st));
+    CU(cudaEventRecord(c->ev_refined, st));
     if (c->timing) CU(cudaEventRecord(c->ev[3], st));
     return run_dibr(c, fl, fr, d_interlaced, st);
 }
@@ -1172,9 +1179,12 @@ static int process_host(s2mv_ctx *c, const uint8_t *img_sbs, int num_cols_sbs, f
     }
     if (two_res) TRY(run_frame_2(c, c->sbs, num_cols_sbs, c->dispF[0], c->dispF[1], c->interlaced, st));
     else TRY(run_frame(c, c->sbs, num_cols_sbs, c->dispF[0], c->dispF[1], c->interlaced, false, st));
-    if (disp_l) CU(cudaMemcpyAsync(pin_dl ? disp_l : c->h_disp[0], c->dispF[0], n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (disp_r) CU(cudaMemcpyAsync(pin_dr ? disp_r : c->h_disp[1], c->dispF[1], n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    // the disparity maps are final before DIBR starts: their D2H runs on a second stream underneath it
+    CU(cudaStreamWaitEvent(c->st_aux, c->ev_refined, 0));
+    if (disp_l) CU(cudaMemcpyAsync(pin_dl ? disp_l : c->h_disp[0], c->dispF[0], n * sizeof(float), cudaMemcpyDeviceToHost, c->st_aux));
+    if (disp_r) CU(cudaMemcpyAsync(pin_dr ? disp_r : c->h_disp[1], c->dispF[1], n * sizeof(float), cudaMemcpyDeviceToHost, c->st_aux));
     if (interlaced) CU(cudaMemcpyAsync(pin_out ? interlaced : c->h_interlaced, c->interlaced, out_bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(c->st_aux));
     CU(cudaStreamSynchronize(st));
     if (disp_l && !pin_dl) memcpy(disp_l, c->h_disp[0], n * sizeof(float));
     if (disp_r && !pin_dr) memcpy(disp_r, c->h_disp[1], n * sizeof(float));

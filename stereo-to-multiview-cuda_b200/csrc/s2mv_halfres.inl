@@ -60,6 +60,7 @@ static int run_frame_2(s2mv_ctx *c, const uint8_t *d_sbs, int num_cols_sbs, floa
     k_disp_scale<<<g, 256, 0, st>>>(fr, lo->dispF[1], H, W, Hd, Wd, inv);
     KCHECK();
     c->launches += 2;
+    CU(cudaEventRecord(c->ev_refined, st));
     if (c->timing) CU(cudaEventRecord(c->ev[3], st));
     TRY(run_dibr(c, fl, fr, d_interlaced, st));
     c->launches += lo->launches;
