@@ -57,6 +57,19 @@ METRIC = "1080p D=128 stereo->8-view frames/s"
 BAND_ROWS = 135  # bounded CPU sample: 1/8 of the frame
 
 
+WORKLOAD3 = ("config3: synthetic 1080p stereo stream (generator of stereo-to-multiview-cuda_b200/synth.py, seeds 1000+i, "
+             "4 distinct frames per rank cycled), D=128, zd=64, 8 views, angle 18")
+
+
+def load_frames(workload, rank=0):
+    """The frames one rank cycles through: config2 = the one bundled pair, config3 = synthetic stream frames."""
+    if workload == "config2":
+        return [load_frame()], WORKLOAD
+    import s2mv_b200  # noqa: F401
+    from s2mv_b200_pkg import synth
+    return [synth.make_sbs(H, W, 1000 + 4 * rank + i) for i in range(4)], WORKLOAD3
+
+
 def load_frame():
     import s2mv_b200  # noqa: F401
     from s2mv_b200_pkg import synth
@@ -129,7 +142,8 @@ def run_reference_arm(args):
         return 0
     import oracle_py
     oracle_py.build()
-    sbs = load_frame()
+    frames, workload = load_frames(args.workload)
+    sbs = frames[0]
     for _ in range(args.warmup):
         cpu_sample(sbs)
     t = 0.0
@@ -143,7 +157,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "bundled fish pair, upscaled (synthetic size)",
-        "config": {"workload": WORKLOAD, "step": sample},
+        "config": {"workload": workload, "step": sample},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -158,6 +172,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
+                    help="config2 (default, the headline): the bundled pair at 1080p; config3: synthetic 1080p stream")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -178,17 +194,19 @@ def main():
     sharding.init_process_group("nccl")
     K, Wm = args.steps, max(args.warmup, 3)
 
-    sbs = load_frame()
+    frames, workload = load_frames(args.workload, rank)
+    sbs = frames[0]
+    NF = len(frames)
     pipe = s2mv_b200.Pipeline(local_rank, num_rows=H, num_cols=W, num_disp=D, zero_disp=ZD, num_views=V, angle=18, **ALGO)
     stream = torch.cuda.current_stream().cuda_stream
-    d_sbs = torch.from_numpy(sbs).to(dev)
+    d_frames = [torch.from_numpy(f).to(dev) for f in frames]
     d_dl = torch.empty((H, W), dtype=torch.float32, device=dev)
     d_dr = torch.empty_like(d_dl)
     d_out = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    def step_device():
-        pipe.process_device(d_sbs.data_ptr(), 2 * W, d_dl.data_ptr(), d_dr.data_ptr(), d_out.data_ptr(), stream)
+    def step_device(i=0):
+        pipe.process_device(d_frames[i % NF].data_ptr(), 2 * W, d_dl.data_ptr(), d_dr.data_ptr(), d_out.data_ptr(), stream)
 
     # ---- device-resident throughput ------------------------------------
     for _ in range(Wm):
@@ -206,7 +224,7 @@ def main():
     for i in range(K):
         flush.fill_(i & 0xff)                      # L2 flush between timed iterations (not timed)
         ev[i][0].record()
-        step_device()
+        step_device(i)
         ev[i][1].record()
         ev[i][1].synchronize()
         for k, v in pipe.last_timings().items():
@@ -221,18 +239,18 @@ def main():
     fps, total_frames, slowest_s = sharding.aggregate_throughput(K, dev_ms / 1e3, dev)
 
     # ---- end to end through the host-buffer C-ABI call -------------------
-    h_sbs = torch.from_numpy(sbs).pin_memory()
+    h_frames = [torch.from_numpy(f).pin_memory() for f in frames]
     h_dl = torch.empty((H, W), dtype=torch.float32).pin_memory()
     h_dr = torch.empty((H, W), dtype=torch.float32).pin_memory()
     h_out = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
-    np_in, np_dl, np_dr, np_out = h_sbs.numpy(), h_dl.numpy(), h_dr.numpy(), h_out.numpy()
+    np_ins, np_dl, np_dr, np_out = [h.numpy() for h in h_frames], h_dl.numpy(), h_dr.numpy(), h_out.numpy()
     for _ in range(Wm):
-        pipe.adcensus_stm_into(np_in, np_dl, np_dr, np_out)
+        pipe.adcensus_stm_into(np_ins[0], np_dl, np_dr, np_out)
     sharding.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(K):
-        pipe.adcensus_stm_into(np_in, np_dl, np_dr, np_out)   # synchronous: returns after the D2H copies
+    for i in range(K):
+        pipe.adcensus_stm_into(np_ins[i % NF], np_dl, np_dr, np_out)   # synchronous: returns after the D2H copies
     torch.cuda.synchronize()
     e2e_sync_s = time.perf_counter() - t0
     sharding.barrier()
@@ -247,10 +265,10 @@ def main():
 
     def stream_run(n):
         got = None
-        for _ in range(n):
+        for i in range(n):
             if pipe.stream_pending == DEPTH:
                 got = pipe.stream_collect(copy=False)
-            np.copyto(pipe.stream_input_buffer(), np_in)   # stands in for the decoder writing the frame
+            np.copyto(pipe.stream_input_buffer(), np_ins[i % NF])   # stands in for the decoder writing the frame
             pipe.stream_submit(None)
         while pipe.stream_pending:
             got = pipe.stream_collect(copy=False)
@@ -303,8 +321,9 @@ def main():
     print(json.dumps({
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": 1e3 * slowest_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "bundled fish pair upscaled to 1080p (no published dataset for this path)",
-        "config": {"workload": WORKLOAD, "parallelism": f"frame-parallel x{world}, no collectives",
+        "dtype": "f32", "data": ("bundled fish pair upscaled to 1080p (no published dataset for this path)"
+                                 if args.workload == "config2" else "synthetic stereo stream (no published dataset for this path)"),
+        "config": {"workload": workload, "parallelism": f"frame-parallel x{world}, no collectives",
                    "l2": "256 MB flush write between timed steps; per-frame volume traffic >> L2"},
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(sbs.nbytes),
                 "d2h_bytes_per_step": int(np_dl.nbytes + np_dr.nbytes + np_out.nbytes),
