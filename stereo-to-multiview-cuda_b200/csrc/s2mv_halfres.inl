@@ -17,10 +17,18 @@ extern "C" int s2mv_configure_2(s2mv_ctx *c, const s2mv_params *p, int num_rows_
     q.num_rows = q.num_rows_out = num_rows_disp;
     q.num_cols = q.num_cols_out = num_cols_disp;
     c->lo->chunk_seq_mode = c->chunk_seq_mode;
-    TRY(configure_impl(c->lo, &q, nullptr));
-    CU(cudaSetDevice(c->device));
-    for (int v = 0; v < 2; ++v) TRY(dev_alloc_t(c, &c->lo_bgr[v], (size_t)num_rows_disp * num_cols_disp * 3));
-    return S2MV_OK;
+    st = configure_impl(c->lo, &q, nullptr);
+    if (st == S2MV_OK) {
+        cudaSetDevice(c->device);
+        for (int v = 0; v < 2 && st == S2MV_OK; ++v)
+            st = dev_alloc_t(c, &c->lo_bgr[v], (size_t)num_rows_disp * num_cols_disp * 3);
+    }
+    if (st != S2MV_OK) {  // leave no half-built two-resolution context behind
+        s2mv_destroy(c->lo);
+        c->lo = nullptr;
+        c->configured = false;
+    }
+    return st;
 }
 
 static int run_frame_2(s2mv_ctx *c, const uint8_t *d_sbs, int num_cols_sbs, float *d_disp_l, float *d_disp_r,
