@@ -858,7 +858,9 @@ static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2],
     // lists longer than 1/32 of the image take the dense path (decided on the device, per iteration and view)
     const bool dense_ok = c->irv_hseg[0] && c->irv_nbp >= a.nbins && (size_t)H * W == (size_t)c->prm.num_rows * c->prm.num_cols;
     a.nbp = c->irv_nbp;
-    a.dense_min = (int)(n / 32) + 1;  // measured crossover of the two paths: a list of about n/28
+    // measured crossover of the two paths at 128 bins: a list of about n/28; the dense path's cost grows with
+    // the bin count (bytes per pixel histogram), the sparse one's does not
+    a.dense_min = (int)(n / 32) * (c->irv_nbp > 128 ? c->irv_nbp / 128 : 1) + 1;
     if (const char *e = getenv("S2MV_IRV_DENSE_MIN")) a.dense_min = atoi(e);  // test hook: 0 = always dense, huge = never
     for (int v = 0; v < nviews; ++v) a.hseg[v] = dense_ok ? c->irv_hseg[v] : nullptr;
     for (int it = 0; it < iterations; ++it) {
