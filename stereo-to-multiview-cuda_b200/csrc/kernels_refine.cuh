@@ -56,6 +56,8 @@ struct IrvArgs {
     int *count[2];       // length of list
     int *next_count[2];  // length of next
     int *ticket[2];      // next list entry to hand out (k_irv_vote_dense); reset by k_irv_apply
+    int *accepted[2];    // [iteration]: votes k_irv_apply accepted in that iteration (null: not tracked)
+    int it;              // iteration of this launch
     int H, W, nbins, zd, usd, thresh_s;
     float thresh_h;
     // dense path (k_irv_hseg + k_irv_vote_dense): per-pixel histograms of the horizontal arm span
@@ -64,6 +66,13 @@ struct IrvArgs {
     int dense_min;       // list length from which an iteration takes the dense path
 };
 constexpr int kNoVote = -0x7fffffff;
+
+// An iteration that accepted no vote left disparities and outlier flags as they were, so every later
+// iteration would recompute the same rejected votes: its kernels return at once (exact, not a heuristic).
+__device__ __forceinline__ bool irv_settled(const IrvArgs &a, int v)
+{
+    return a.accepted[v] != nullptr && a.it > 0 && a.accepted[v][a.it - 1] == 0;
+}
 
 // append `mine` items per lane to a global list with one atomic per warp; returns this lane's base
 __device__ __forceinline__ int warp_append_base(int *counter, int mine)
@@ -122,6 +131,7 @@ k_irv_vote(const IrvArgs a)
     const int v = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int *hist = hist_all + warp * a.nbins;
+    if (irv_settled(a, v)) return;
     const int count = *a.count[v];
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.next_count[v] = 0;  // consumed by k_irv_apply, which runs after
     if (a.hseg[v] && count >= a.dense_min) return;                  // this iteration is k_irv_vote_dense's
@@ -214,7 +224,7 @@ k_irv_hseg(const IrvArgs a)
 {
     extern __shared__ __align__(16) uint8_t hs[];  // [kHsegThreads][nbp + 4]: the pad staggers the banks
     const int v = blockIdx.y;
-    if (*a.count[v] < a.dense_min) return;
+    if (irv_settled(a, v) || *a.count[v] < a.dense_min) return;
     constexpr int nbp = 128 * NW, pitch = nbp + 4;
     const int W = a.W;
     const int tiles_x = (W + kHsegThreads - 1) / kHsegThreads, ntiles = tiles_x * a.H;
@@ -262,6 +272,7 @@ k_irv_vote_dense(const IrvArgs a)
 {
     const int v = blockIdx.y;
     const int lane = threadIdx.x & 31;
+    if (irv_settled(a, v)) return;
     const int count = *a.count[v];
     if (count < a.dense_min) return;
     const float *__restrict__ disp = a.disp[v];
@@ -326,9 +337,11 @@ __global__ void __launch_bounds__(256)
 k_irv_apply(const IrvArgs a)
 {
     const int v = blockIdx.y;
+    if (irv_settled(a, v)) return;
     const int count = *a.count[v];
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.ticket[v] = 0;  // for the next iteration's vote
     const int stride = gridDim.x * blockDim.x;
+    int taken = 0;
     for (int e0 = blockIdx.x * blockDim.x; e0 < count; e0 += stride) {  // block-uniform trip count
         const int e = e0 + threadIdx.x;
         int pix = -1;
@@ -339,10 +352,15 @@ k_irv_apply(const IrvArgs a)
                 a.outliers[v][pix] = 0;
                 a.disp[v][pix] = (float)vote;
                 pix = -1;
+                ++taken;
             }
         }
         const int pos = warp_append_base(a.next_count[v], pix >= 0 ? 1 : 0);
         if (pix >= 0) a.next[v][pos] = pix;
+    }
+    if (a.accepted[v] != nullptr) {
+        taken = __reduce_add_sync(0xffffffffu, taken);
+        if ((threadIdx.x & 31) == 0 && taken) atomicAdd(a.accepted[v] + a.it, taken);
     }
 }
 

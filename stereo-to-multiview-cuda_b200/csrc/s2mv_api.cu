@@ -543,7 +543,7 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
             c->irv_nbp = nbp;
         }
     }
-    TRY(dev_alloc_t(c, &c->irv_count, 8));
+    TRY(dev_alloc_t(c, &c->irv_count, 8 + 2 * 64));
     if (band) {
         TRY(dev_alloc_t(c, &c->band_flags, 4));
         CU(cudaMemset(c->band_flags, 0, 4 * sizeof(unsigned int)));
@@ -845,13 +845,14 @@ static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2],
         a.list[v] = c->irv_list[v]; a.next[v] = c->irv_list2[v]; a.vote[v] = c->irv_vote[v];
         a.count[v] = c->irv_count + v; a.next_count[v] = c->irv_count + 2 + v;
         a.ticket[v] = c->irv_count + 4 + v;
+        a.accepted[v] = iterations <= 64 ? c->irv_count + 8 + 64 * v : nullptr;
     }
     a.H = H; a.W = W; a.nbins = D > 65 ? D : 65; a.zd = zd; a.usd = usd; a.thresh_s = thresh_s; a.thresh_h = thresh_h;
     const size_t hist_bytes = (size_t)kIrvWarps * a.nbins * sizeof(int);
     if (hist_bytes > 64 * 1024) return fail(S2MV_ERR_BAD_PARAM, "num_disp too large for the voting histogram");
     if (iterations <= 0) return S2MV_OK;
     // outliers -> list, once; every iteration then votes on its list and leaves the survivors as the next one
-    CU(cudaMemsetAsync(c->irv_count, 0, 8 * sizeof(int), st));
+    CU(cudaMemsetAsync(c->irv_count, 0, (8 + 2 * 64) * sizeof(int), st));
     k_irv_compact<<<dim3((unsigned)((n + 4095) / 4096), nviews), 256, 0, st>>>(a);
     KCHECK();
     c->launches += 1;
@@ -864,6 +865,7 @@ static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2],
     if (const char *e = getenv("S2MV_IRV_DENSE_MIN")) a.dense_min = atoi(e);  // test hook: 0 = always dense, huge = never
     for (int v = 0; v < nviews; ++v) a.hseg[v] = dense_ok ? c->irv_hseg[v] : nullptr;
     for (int it = 0; it < iterations; ++it) {
+        a.it = it;
         if (dense_ok) {
             {
                 const dim3 gh(c->sm_count * 8, nviews);
