@@ -134,22 +134,30 @@ __device__ __forceinline__ int max_abs_diff3(uint32_t a, uint32_t b)
 // Both views in one launch, pixels staged in shared memory: the walk is a chain of up to 4*usd dependent
 // loads; out of L2 each step costs ~600 cycles, out of shared memory ~30.
 constexpr int kArmW = 64, kArmH = 16;
+// The colour differences are integers, so the reference's float tests (float)v > t are evaluated as
+// v > floor(t) on integers (arm_threshold): the two int->float conversions per step ran on the quarter-rate
+// conversion pipe and were what bounded this kernel (ncu: math-pipe throttle 5 of 7.7 stall slots per issue).
+__device__ __forceinline__ int arm_threshold(float t)
+{
+    return (int)floorf(fminf(fmaxf(t, -1.0f), 1.0e9f));  // any t < 0 passes every test, any t >= 255 none
+}
+
 __device__ __forceinline__ int arm_walk_tile(const uint32_t *__restrict__ t, int pitch, int x, int y, int dx, int dy,
-                                             uint32_t anchor, float ucd, float lcd, int usd, int lsd, int H, int W)
+                                             uint32_t anchor, int ucd_i, int lcd_i, int usd, int lsd, int H, int W)
 {
     uint32_t prev = anchor;
     int arm = 0;
     const int step = dy * pitch + dx;
-    for (int s = 1; s <= usd; ++s) {
-        const int cx = x + dx * s, cy = y + dy * s;
-        if (cx < 0 || cx > W - 1 || cy < 0 || cy > H - 1) break;
+    // steps that stay inside the image (the reference tests the coordinates every step)
+    const int limit = min(usd, dx ? (dx > 0 ? W - 1 - x : x) : (dy > 0 ? H - 1 - y : y));
+    for (int s = 1; s <= limit; ++s) {
         arm = s;
         const uint32_t c = t[s * step];
-        const float ac = (float)max_abs_diff3(c, anchor), cp = (float)max_abs_diff3(c, prev);
+        const int ac = max_abs_diff3(c, anchor), cp = max_abs_diff3(c, prev);
         if (s > lsd) {
-            if (ac > ucd) break;
+            if (ac > ucd_i) break;
         } else {
-            if (ac > lcd || cp > lcd) break;
+            if (ac > lcd_i || cp > lcd_i) break;
         }
         prev = c;
     }
@@ -176,10 +184,11 @@ k_arms_tile(const uint32_t *__restrict__ pix0, const uint32_t *__restrict__ pix1
     if (x >= W || y >= H) return;
     const uint32_t *__restrict__ t = atile + (threadIdx.y + usd) * TW + threadIdx.x + usd;
     const uint32_t a = *t;
-    const int u = arm_walk_tile(t, TW, x, y, 0, -1, a, ucd, lcd, usd, lsd, H, W);
-    const int d = arm_walk_tile(t, TW, x, y, 0, +1, a, ucd, lcd, usd, lsd, H, W);
-    const int l = arm_walk_tile(t, TW, x, y, -1, 0, a, ucd, lcd, usd, lsd, H, W);
-    const int r = arm_walk_tile(t, TW, x, y, +1, 0, a, ucd, lcd, usd, lsd, H, W);
+    const int ui = arm_threshold(ucd), li = arm_threshold(lcd);
+    const int u = arm_walk_tile(t, TW, x, y, 0, -1, a, ui, li, usd, lsd, H, W);
+    const int d = arm_walk_tile(t, TW, x, y, 0, +1, a, ui, li, usd, lsd, H, W);
+    const int l = arm_walk_tile(t, TW, x, y, -1, 0, a, ui, li, usd, lsd, H, W);
+    const int r = arm_walk_tile(t, TW, x, y, +1, 0, a, ui, li, usd, lsd, H, W);
     arms[(size_t)y * W + x] = (uint32_t)u | ((uint32_t)d << 8) | ((uint32_t)l << 16) | ((uint32_t)r << 24);
 }
 
