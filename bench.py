@@ -257,6 +257,23 @@ def main():
     e2e_sync_fps, _, _ = sharding.aggregate_throughput(K, e2e_sync_s, dev)
     assert np.array_equal(np_out, d_out.cpu().numpy()), "host and device entry points disagree"
 
+    # ---- the same call with PAGEABLE caller buffers (what an unchanged video_io.cpp passes) ----
+    pg_in = [np.array(f) for f in frames]
+    pg_dl, pg_dr, pg_out = np.empty((H, W), np.float32), np.empty((H, W), np.float32), np.empty((H, W, 3), np.uint8)
+    pageable = {}
+    for mode in ("staged", "registered"):
+        pipe.set_host_registration(mode == "registered")
+        for _ in range(Wm):
+            pipe.adcensus_stm_into(pg_in[0], pg_dl, pg_dr, pg_out)
+        sharding.barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            pipe.adcensus_stm_into(pg_in[i % NF], pg_dl, pg_dr, pg_out)
+        dt = time.perf_counter() - t0
+        pageable[mode] = sharding.aggregate_throughput(K, dt, dev)[0]
+        assert np.array_equal(pg_out, np_out)
+    pipe.set_host_registration(False)
+
     # ---- end to end through the asynchronous frame stream (the video loop) ----
     # every frame: host frame -> the slot's pinned buffer -> H2D -> all kernels -> D2H of both disparity
     # maps and the interlaced frame into pinned host memory; copies of neighbouring frames overlap the kernels
@@ -328,7 +345,10 @@ def main():
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(sbs.nbytes),
                 "d2h_bytes_per_step": int(np_dl.nbytes + np_dr.nbytes + np_out.nbytes),
                 "api": f"s2mv_stream_submit/collect, {DEPTH} frames in flight (host frame -> pinned slot -> H2D -> kernels -> D2H)",
-                "synchronous_call": {"value": e2e_sync_fps, "unit": "frames/s", "api": "s2mv_process_sbs (adcensus_stm contract)"}},
+                "synchronous_call": {"value": e2e_sync_fps, "unit": "frames/s", "api": "s2mv_process_sbs (adcensus_stm contract)",
+                                     "pageable_caller_buffers": {"staged_through_pinned": pageable["staged"],
+                                                                 "page_locked_in_place": pageable["registered"],
+                                                                 "unit": "frames/s"}}},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,

@@ -91,6 +91,16 @@ int s2mv_device_sm_count(const s2mv_ctx *ctx);
 int s2mv_process_sbs(s2mv_ctx *ctx, const uint8_t *img_sbs, int num_cols_sbs,
                      float *disp_l, float *disp_r, uint8_t *interlaced);
 
+/* Pageable caller buffers (cv::Mat::data in the reference's drivers) are normally staged through the
+ * context's pinned buffers: two extra host copies of 35 MB per 1080p frame (136 instead of 214 frames/s).  With
+ * host registration on, each distinct caller buffer is page-locked in place the first time it is seen
+ * (cudaHostRegister) and DMA'd directly from then on.  CONTRACT: every buffer passed while it is on must stay
+ * allocated until the context is destroyed or registration is switched off (which unregisters everything) --
+ * memory freed while registered and handed out again by the allocator would be written through a stale
+ * mapping.  For callers that reuse their buffers across frames, as the reference's video loop does.  Off by
+ * default; the adcensus_stm shims switch it on when S2MV_HOST_REGISTER=1 is in the environment. */
+int s2mv_set_host_registration(s2mv_ctx *ctx, int on);
+
 /* Same work on DEVICE pointers, enqueued on `stream` (a cudaStream_t; NULL =
  * the context's own stream) without synchronising. */
 int s2mv_process_sbs_device(s2mv_ctx *ctx, const uint8_t *d_img_sbs, int num_cols_sbs,

@@ -31,7 +31,7 @@ EXPORTED_SYMBOLS = [
     "s2mv_configure_band", "s2mv_band_info", "s2mv_band_prepare", "s2mv_band_pass", "s2mv_band_halo",
     "s2mv_band_disp", "s2mv_band_finish", "s2mv_band_connect", "s2mv_band_ipc_export", "s2mv_band_ipc_connect",
     "s2mv_band_status", "s2mv_dc_so", "s2mv_enable_so",
-    "s2mv_configure_2", "s2mv_process_sbs_2", "s2mv_process_sbs_2_device",
+    "s2mv_configure_2", "s2mv_process_sbs_2", "s2mv_process_sbs_2_device", "s2mv_set_host_registration",
 ]
 # the reference's own C++ symbols exported as shims (include/s2mv_compat.h)
 COMPAT_SYMBOLS = [
@@ -197,6 +197,10 @@ class Pipeline:
     @property
     def last_launch_count(self):
         return self._L.s2mv_last_launch_count(self._ctx)
+
+    def set_host_registration(self, on=True):
+        """Page-lock pageable caller buffers in place (once per buffer) instead of staging them every call."""
+        _check(self._L.s2mv_set_host_registration(self._ctx, int(on)))
 
     def enable_timing(self, on=True):
         _check(self._L.s2mv_enable_timing(self._ctx, int(on)))

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <utility>
 #include <vector>
 
 #include "../../include/s2mv.h"
@@ -271,6 +272,9 @@ struct s2mv_ctx {
     float *h_disp[2] = {};
     size_t h_sbs_bytes = 0;
     // timing
+    // caller buffers page-locked in place (s2mv_set_host_registration): address -> bytes
+    bool host_reg = false;
+    std::vector<std::pair<const void *, size_t>> host_regs;
     cudaEvent_t ev_refined = nullptr;   // disparities final (before DIBR): the synchronous call starts their D2H here
     cudaStream_t st_aux = nullptr;      // second copy stream of the synchronous host call
     cudaEvent_t ev[5] = {};
@@ -289,6 +293,7 @@ struct s2mv_ctx {
     int stream_cols_sbs = 0, slot_head = 0, slot_tail = 0, slots_pending = 0;
 };
 static void stream_release(s2mv_ctx *c);
+static void host_unregister_all(s2mv_ctx *c);
 
 static int dev_alloc(s2mv_ctx *c, void **p, size_t bytes)
 {
@@ -365,6 +370,7 @@ extern "C" void s2mv_destroy(s2mv_ctx *c)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
         if (c->kev[i]) cudaEventDestroy(c->kev[i]);
     }
+    host_unregister_all(c);
     if (c->ev_refined) cudaEventDestroy(c->ev_refined);
     if (c->st_aux) cudaStreamDestroy(c->st_aux);
     cudaStreamDestroy(c->stream);
@@ -1133,6 +1139,62 @@ extern "C" int s2mv_costvol_device(s2mv_ctx *c, const uint8_t *d_img_sbs, int nu
 static int run_frame_2(s2mv_ctx *c, const uint8_t *d_sbs, int num_cols_sbs, float *d_disp_l, float *d_disp_r,
                        uint8_t *d_interlaced, cudaStream_t st);
 
+static void host_unregister_all(s2mv_ctx *c)
+{
+    for (auto &r : c->host_regs) cudaHostUnregister(const_cast<void *>(r.first));
+    cudaGetLastError();
+    c->host_regs.clear();
+}
+
+// Page-lock a pageable caller buffer in place so that it can be DMA'd without the staging copy.  The
+// reference's video driver hands the same cv::Mat buffers to adcensus_stm for its whole run
+// (video_io.cpp:125-137), so this happens once per buffer.  Returns false (-> staging) when the range cannot
+// be registered; a stale overlapping registration (the caller freed and reallocated) is dropped and retried.
+static bool host_register(s2mv_ctx *c, const void *ptr, size_t bytes)
+{
+    for (auto &r : c->host_regs)
+        if (r.first == ptr && r.second >= bytes) return true;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        cudaError_t e = cudaHostRegister(const_cast<void *>(ptr), bytes, cudaHostRegisterDefault);
+        if (e == cudaSuccess) {
+            if (c->host_regs.size() >= 16) {  // keep the table small: drop the oldest
+                cudaHostUnregister(const_cast<void *>(c->host_regs.front().first));
+                c->host_regs.erase(c->host_regs.begin());
+            }
+            c->host_regs.emplace_back(ptr, bytes);
+            return true;
+        }
+        cudaGetLastError();
+        if (e != cudaErrorHostMemoryAlreadyRegistered) return false;
+        // overlaps something registered earlier (by this table or by the caller): forget ours that overlap, retry once
+        const char *lo = (const char *)ptr, *hi = lo + bytes;
+        bool dropped = false;
+        for (size_t i = 0; i < c->host_regs.size();) {
+            const char *a = (const char *)c->host_regs[i].first, *b = a + c->host_regs[i].second;
+            if (a < hi && lo < b) {
+                cudaHostUnregister(const_cast<void *>(c->host_regs[i].first));
+                c->host_regs.erase(c->host_regs.begin() + i);
+                dropped = true;
+            } else ++i;
+        }
+        cudaGetLastError();
+        if (!dropped) return false;
+    }
+    return false;
+}
+
+extern "C" int s2mv_set_host_registration(s2mv_ctx *c, int on)
+{
+    if (!c) return fail(S2MV_ERR_BAD_PARAM, "null ctx");
+    CU(cudaSetDevice(c->device));
+    if (!on) {
+        CU(cudaStreamSynchronize(c->stream));
+        host_unregister_all(c);
+    }
+    c->host_reg = on != 0;
+    return S2MV_OK;
+}
+
 // host buffers in / out, synchronous: s2mv_process_sbs (adcensus_stm) and s2mv_process_sbs_2 (adcensus_stm_2)
 static int process_host(s2mv_ctx *c, const uint8_t *img_sbs, int num_cols_sbs, float *disp_l, float *disp_r,
                         uint8_t *interlaced, bool two_res)
@@ -1173,8 +1235,13 @@ static int process_host(s2mv_ctx *c, const uint8_t *img_sbs, int num_cols_sbs, f
         cudaGetLastError();
         return ok;
     };
-    const bool pin_in = is_pinned(img_sbs), pin_dl = is_pinned(disp_l), pin_dr = is_pinned(disp_r),
-               pin_out = is_pinned(interlaced);
+    bool pin_in = is_pinned(img_sbs), pin_dl = is_pinned(disp_l), pin_dr = is_pinned(disp_r), pin_out = is_pinned(interlaced);
+    if (c->host_reg) {  // pageable buffers are page-locked in place once and DMA'd directly from then on
+        if (!pin_in) pin_in = host_register(c, img_sbs, sbs_bytes);
+        if (disp_l && !pin_dl) pin_dl = host_register(c, disp_l, n * sizeof(float));
+        if (disp_r && !pin_dr) pin_dr = host_register(c, disp_r, n * sizeof(float));
+        if (interlaced && !pin_out) pin_out = host_register(c, interlaced, out_bytes);
+    }
     if (pin_in) {
         CU(cudaMemcpyAsync(c->sbs, img_sbs, sbs_bytes, cudaMemcpyHostToDevice, st));
     } else {

@@ -235,3 +235,29 @@ def test_region_voting_dense_and_sparse_paths_agree_with_oracle(s2mv, oracle, bu
         sbs = np.ascontiguousarray(np.concatenate([bud_sbs[100:228, :320], bud_sbs[100:228, 640:960]], 1))
         got, want = run_both(p, oracle, sbs, 320, 96, 40)
         assert_frame_equal(got, want)
+
+
+def test_host_registration_of_pageable_buffers(s2mv):
+    # pageable numpy buffers: staged by default, page-locked in place with host registration on; the same
+    # bytes either way, repeated calls reuse the registration, switching it off releases everything
+    from s2mv_b200_pkg import synth
+    H, W, D, zd = 96, 320, 32, 16
+    frames = [synth.make_sbs(H, W, 900 + i) for i in range(3)]
+    with s2mv.Pipeline(0, num_rows=H, num_cols=W, num_disp=D, zero_disp=zd, num_views=8, angle=18, **ALGO) as p:
+        want = [p.adcensus_stm(f) for f in frames]
+        p.set_host_registration(True)
+        dl = np.empty((H, W), np.float32); dr = np.empty((H, W), np.float32); out = np.empty((H, W, 3), np.uint8)
+        buf = np.empty_like(frames[0])
+        for rep in range(2):
+            for f, w in zip(frames, want):
+                buf[...] = f                                   # the caller's one reused frame buffer
+                p.adcensus_stm_into(buf, dl, dr, out)
+                assert np.array_equal(dl, w[0]) and np.array_equal(dr, w[1]) and np.array_equal(out, w[2])
+        keep = [f.copy() for f in frames]                      # more buffers, all alive while registered (the contract)
+        outs = [(np.empty((H, W), np.float32), np.empty((H, W), np.float32), np.empty((H, W, 3), np.uint8)) for _ in frames]
+        for f, o, w in zip(keep, outs, want):
+            p.adcensus_stm_into(f, *o)
+            assert all(np.array_equal(a, b) for a, b in zip(o, w))
+        p.set_host_registration(False)                         # unregisters everything; staging again
+        got = p.adcensus_stm(frames[0])
+        assert all(np.array_equal(a, b) for a, b in zip(got, want[0]))
