@@ -140,6 +140,9 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # torchrun pins OMP_NUM_THREADS=1 in every worker; this arm is rank 0 alone on the host's cores
+    if "TORCHELASTIC_RUN_ID" in os.environ or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import oracle_py
     oracle_py.build()
     frames, workload = load_frames(args.workload)
