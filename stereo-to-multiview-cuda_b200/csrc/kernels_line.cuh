@@ -509,7 +509,7 @@ __global__ void k_band_signal(unsigned int *peer_flag, unsigned int epoch)
 __global__ void k_band_wait(const unsigned int *flag, unsigned int epoch, unsigned int *status)
 {
     unsigned int v = 0;
-    for (long long spin = 0; spin < 4000000; ++spin) {  // ~4 s at 1 us per probe
+    for (long long spin = 0; spin < 20000000; ++spin) {  // ~20 s at 1 us per probe: a late neighbour, not a lost one
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if ((int)(v - epoch) >= 0) return;
         __nanosleep(1000);

@@ -321,6 +321,10 @@ class DistBand:
     def close(self):
         self.ctx.close()
 
+    def check(self):
+        """Raise if any wait of this band ran out before its neighbour arrived (synchronises the stream)."""
+        self.ctx.status(self.torch.cuda.current_stream().cuda_stream)
+
     def process(self, d_sbs, num_cols_sbs, phases=None):
         """d_sbs: the whole SBS frame on this rank's GPU.  Returns this band's rows of
         (disp_l, disp_r, interlaced); everything is enqueued on torch's current stream.  `phases`: a dict that

@@ -94,6 +94,8 @@ def main():
         b.synchronize()
         ms += sharding.reduce_scalar(a.elapsed_time(b), "max", dev)
     ms /= args.steps
+    if band.transport == "p2p":
+        band.check()                            # no wait ran out before its neighbour arrived
     phases = {}
     band.process(d_sbs, 2 * W, phases)          # one more frame with per-phase device times (this rank's)
     allph = [None] * world
