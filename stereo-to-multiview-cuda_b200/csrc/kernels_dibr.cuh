@@ -168,12 +168,21 @@ struct DbmArgs {
     int H, W;
 };
 
-__device__ __forceinline__ uint32_t warp_fetch(const uint32_t *__restrict__ pixrow, float disp, float shift, int tx, int W)
+// The conversions of this kernel (28 per pixel and view) ran on the quarter-rate conversion pipe and bounded
+// it (ncu: 82 % of that pipe).  They are all between small non-negative integers and floats, so they are done
+// on the FP32 pipe with the 2^23 bias instead, bit for bit:
+//   (float)n       = as_float(0x4b000000 | n) - 2^23                    for 0 <= n < 2^23
+//   (uint)trunc(v) = as_uint(v + 2^23, rounded toward zero) & 0x7fffff   for 0 <= v < 2^23
+constexpr float kTwo23 = 8388608.0f;
+__device__ __forceinline__ float small_to_float(uint32_t n) { return __fsub_rn(__uint_as_float(0x4b000000u | n), kTwo23); }
+__device__ __forceinline__ uint32_t trunc_bits(float v) { return __float_as_uint(__fadd_rz(v, kTwo23)); }
+
+__device__ __forceinline__ uint32_t warp_fetch(const uint32_t *__restrict__ pixrow, float disp, float shift, float ftx, int W)
 {
     // PTX of the reference: fma.rn(shift, disp, (float)tx); max 0; min W-1; cvt.rzi
-    float fx = __fmaf_rn(shift, disp, (float)tx);
-    fx = fminf(fmaxf(fx, 0.0f), (float)(W - 1));
-    return pixrow[(int)fx];  // bilinear at integral coordinates = plain fetch (Q23)
+    float fx = __fmaf_rn(shift, disp, ftx);
+    fx = fminf(fmaxf(fx, 0.0f), small_to_float((uint32_t)(W - 1)));
+    return pixrow[trunc_bits(fx) & 0x7fffffu];  // bilinear at integral coordinates = plain fetch (Q23)
 }
 
 __global__ void __launch_bounds__(256)
@@ -185,19 +194,24 @@ k_dbm(const DbmArgs a)
     const int vi = blockIdx.z;
     const float shift = a.shift[vi];
     const size_t row = (size_t)ty * a.W, i = row + tx;
-    const float mr = a.maskR[i], ml = a.maskL[i], m = a.tmask[i];
-    const uint32_t pl = warp_fetch(a.pixL + row, a.dispR[i], -shift, tx, a.W);
-    const uint32_t pr = warp_fetch(a.pixR + row, a.dispL[i], (float)(1.0 - (double)shift), tx, a.W);
-    const float im = __fsub_rn(1.0f, m);
+    // masks are sums of non-negative weights; a (never observed) negative or NaN product must still convert
+    // to 0 as cvt.rzi.u32 does, hence the max with 0 on the mask factors
+    const float mr = fmaxf(a.maskR[i], 0.0f), ml = fmaxf(a.maskL[i], 0.0f), m = fmaxf(a.tmask[i], 0.0f);
+    const float ftx = small_to_float((uint32_t)tx);
+    const uint32_t pl = warp_fetch(a.pixL + row, a.dispR[i], -shift, ftx, a.W);
+    const uint32_t pr = warp_fetch(a.pixR + row, a.dispL[i], (float)(1.0 - (double)shift), ftx, a.W);
+    const float im = fmaxf(__fsub_rn(1.0f, a.tmask[i]), 0.0f);
     uint8_t *o = a.views + ((size_t)a.view_index[vi] * a.H * a.W + i) * 3;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const float cl = (float)((pl >> (8 * c)) & 0xff), cr = (float)((pr >> (8 * c)) & 0xff);
-        const uint32_t wl = __float2uint_rz(__fmul_rn(cl, mr)) & 0xff;  // warped left, masked by mask_r
-        const uint32_t wr = __float2uint_rz(__fmul_rn(cr, ml)) & 0xff;  // warped right, masked by mask_l
-        const uint32_t b = __float2uint_rz(__fmul_rn(im, (float)wl)) & 0xff;
-        const uint32_t q = __float2uint_rz(__fmul_rn(m, (float)wr)) & 0xff;
-        o[c] = (uint8_t)(b + q);
+        // byte c of the pixel under the 2^23 bias: one PRMT
+        const float cl = __fsub_rn(__uint_as_float(__byte_perm(pl, 0x4b000000u, 0x7440 + c)), kTwo23);
+        const float cr = __fsub_rn(__uint_as_float(__byte_perm(pr, 0x4b000000u, 0x7440 + c)), kTwo23);
+        const float wl = small_to_float(trunc_bits(__fmul_rn(cl, mr)) & 0xffu);  // warped left, masked by mask_r
+        const float wr = small_to_float(trunc_bits(__fmul_rn(cr, ml)) & 0xffu);  // warped right, masked by mask_l
+        const uint32_t b = trunc_bits(__fmul_rn(im, wl));
+        const uint32_t q = trunc_bits(__fmul_rn(m, wr));
+        o[c] = (uint8_t)(b + q);                                                   // low bytes add mod 256
     }
 }
 

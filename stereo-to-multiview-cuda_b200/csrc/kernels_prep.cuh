@@ -137,36 +137,57 @@ constexpr int kArmW = 64, kArmH = 16;
 // The colour differences are integers, so the reference's float tests (float)v > t are evaluated as
 // v > floor(t) on integers (arm_threshold): the two int->float conversions per step ran on the quarter-rate
 // conversion pipe and were what bounded this kernel (ncu: math-pipe throttle 5 of 7.7 stall slots per issue).
-__device__ __forceinline__ int arm_threshold(float t)
+__host__ __device__ __forceinline__ int arm_threshold(float t)
 {
     return (int)floorf(fminf(fmaxf(t, -1.0f), 1.0e9f));  // any t < 0 passes every test, any t >= 255 none
 }
 
+// "some colour byte of d exceeds n" for 0 <= n <= 127 without unpacking the bytes: a byte with its top bit set
+// exceeds n; otherwise adding 127 - n to its low seven bits sets the top bit exactly when it does.  k127 holds
+// 127 - n in each of the three colour bytes.
+__device__ __forceinline__ uint32_t over_bits(uint32_t d, uint32_t k127) { return ((d & 0x007f7f7fu) + k127) | d; }
+
+// SWAR: both thresholds lie in [0, 127] (the launcher checks) and the tests run on packed bytes.
+template <bool SWAR>
 __device__ __forceinline__ int arm_walk_tile(const uint32_t *__restrict__ t, int pitch, int x, int y, int dx, int dy,
                                              uint32_t anchor, int ucd_i, int lcd_i, int usd, int lsd, int H, int W)
 {
-    uint32_t prev = anchor;
-    int arm = 0;
     const int step = dy * pitch + dx;
     // steps that stay inside the image (the reference tests the coordinates every step)
     const int limit = min(usd, dx ? (dx > 0 ? W - 1 - x : x) : (dy > 0 ? H - 1 - y : y));
-    for (int s = 1; s <= limit; ++s) {
-        arm = s;
-        const uint32_t c = t[s * step];
-        const int ac = max_abs_diff3(c, anchor), cp = max_abs_diff3(c, prev);
-        if (s > lsd) {
-            if (ac > ucd_i) break;
+    const int near = min(limit, lsd);
+    const uint32_t ku = 0x00010101u * (uint32_t)(127 - ucd_i), kl = 0x00010101u * (uint32_t)(127 - lcd_i);
+    const uint32_t *__restrict__ p = t;
+    uint32_t prev = anchor;
+    int s = 1;
+    // within lsd: the colour must stay close to the anchor and to the previous pixel
+    for (; s <= near; ++s) {
+        p += step;
+        const uint32_t c = *p;
+        if (SWAR) {
+            if ((over_bits(__vabsdiffu4(c, anchor), kl) | over_bits(__vabsdiffu4(c, prev), kl)) & 0x00808080u) return s;
         } else {
-            if (ac > lcd_i || cp > lcd_i) break;
+            if (max_abs_diff3(c, anchor) > lcd_i || max_abs_diff3(c, prev) > lcd_i) return s;
         }
         prev = c;
     }
-    return arm;
+    // beyond lsd: close to the anchor under the other threshold
+    for (; s <= limit; ++s) {
+        p += step;
+        const uint32_t c = *p;
+        if (SWAR) {
+            if (over_bits(__vabsdiffu4(c, anchor), ku) & 0x00808080u) return s;
+        } else {
+            if (max_abs_diff3(c, anchor) > ucd_i) return s;
+        }
+    }
+    return limit;
 }
 
+template <bool SWAR>
 __global__ void __launch_bounds__(kArmW *kArmH)
 k_arms_tile(const uint32_t *__restrict__ pix0, const uint32_t *__restrict__ pix1, uint32_t *__restrict__ arms0,
-            uint32_t *__restrict__ arms1, float ucd, float lcd, int usd, int lsd, int H, int W)
+            uint32_t *__restrict__ arms1, int ui, int li, int usd, int lsd, int H, int W)
 {
     extern __shared__ uint32_t atile[];
     const uint32_t *__restrict__ pix = blockIdx.z ? pix1 : pix0;
@@ -184,11 +205,10 @@ k_arms_tile(const uint32_t *__restrict__ pix0, const uint32_t *__restrict__ pix1
     if (x >= W || y >= H) return;
     const uint32_t *__restrict__ t = atile + (threadIdx.y + usd) * TW + threadIdx.x + usd;
     const uint32_t a = *t;
-    const int ui = arm_threshold(ucd), li = arm_threshold(lcd);
-    const int u = arm_walk_tile(t, TW, x, y, 0, -1, a, ui, li, usd, lsd, H, W);
-    const int d = arm_walk_tile(t, TW, x, y, 0, +1, a, ui, li, usd, lsd, H, W);
-    const int l = arm_walk_tile(t, TW, x, y, -1, 0, a, ui, li, usd, lsd, H, W);
-    const int r = arm_walk_tile(t, TW, x, y, +1, 0, a, ui, li, usd, lsd, H, W);
+    const int u = arm_walk_tile<SWAR>(t, TW, x, y, 0, -1, a, ui, li, usd, lsd, H, W);
+    const int d = arm_walk_tile<SWAR>(t, TW, x, y, 0, +1, a, ui, li, usd, lsd, H, W);
+    const int l = arm_walk_tile<SWAR>(t, TW, x, y, -1, 0, a, ui, li, usd, lsd, H, W);
+    const int r = arm_walk_tile<SWAR>(t, TW, x, y, +1, 0, a, ui, li, usd, lsd, H, W);
     arms[(size_t)y * W + x] = (uint32_t)u | ((uint32_t)d << 8) | ((uint32_t)l << 16) | ((uint32_t)r << 24);
 }
 

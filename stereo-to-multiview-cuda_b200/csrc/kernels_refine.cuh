@@ -468,10 +468,12 @@ k_bilateral4(const float *__restrict__ in0, const float *__restrict__ in1, float
             for (int kx = 0; kx < KW; ++kx) {
                 const float vs = v[o + kx];
                 const float ad = fabsf(__fsub_rn(va[o], vs));
-                int ci;
-                if (BOUNDED) ci = __float_as_int(__fadd_rz(ad, 8388608.0f)) & 0x7fffff;
-                else ci = min((int)ad, ncolour - 1);
-                const float wt = __fmul_rn(w[kx], scol[ci]);
+                // BOUNDED: adding 2^21 toward zero leaves 4 * |a - s| (to a quarter) in the mantissa;
+                // masking the two fraction bits gives the table's byte offset, 4 * floor(|a - s|)
+                int cb;
+                if (BOUNDED) cb = __float_as_int(__fadd_rz(ad, 2097152.0f)) & 0x7ffffc;
+                else cb = 4 * min((int)ad, ncolour - 1);
+                const float wt = __fmul_rn(w[kx], *reinterpret_cast<const float *>(reinterpret_cast<const char *>(scol) + cb));
                 norm[o] = __fadd_rn(norm[o], wt);
                 res[o] = __fmaf_rn(vs, wt, res[o]);
             }

@@ -421,7 +421,8 @@ static int set_kernel_attrs()
     TRY(set_smem(k_irv_hseg<2>, 100 * 1024));
     TRY(set_smem(k_irv_hseg<3>, 100 * 1024));
     TRY(set_smem(k_irv_hseg<4>, 100 * 1024));
-    TRY(set_smem(k_arms_tile, 160 * 1024));
+    TRY(set_smem(k_arms_tile<true>, 160 * 1024));
+    TRY(set_smem(k_arms_tile<false>, 160 * 1024));
     return S2MV_OK;
 }
 
@@ -653,8 +654,12 @@ static int launch_arms(s2mv_ctx *c, const uint32_t *p0, const uint32_t *p1, uint
 {
     if (usd < 0 || usd > 64) return fail(S2MV_ERR_BAD_PARAM, "usd out of range");
     const size_t smem = (size_t)(kArmW + 2 * usd) * (kArmH + 2 * usd) * sizeof(uint32_t);
-    k_arms_tile<<<dim3((W + kArmW - 1) / kArmW, (H + kArmH - 1) / kArmH, nviews), dim3(kArmW, kArmH), smem, st>>>(
-        p0, p1, a0, a1, ucd, lcd, usd, lsd, H, W);
+    const int ui = arm_threshold(ucd), li = arm_threshold(lcd);
+    const dim3 g((W + kArmW - 1) / kArmW, (H + kArmH - 1) / kArmH, nviews), b(kArmW, kArmH);
+    if (ui >= 0 && ui <= 127 && li >= 0 && li <= 127)
+        k_arms_tile<true><<<g, b, smem, st>>>(p0, p1, a0, a1, ui, li, usd, lsd, H, W);
+    else
+        k_arms_tile<false><<<g, b, smem, st>>>(p0, p1, a0, a1, ui, li, usd, lsd, H, W);
     KCHECK();
     c->launches += 1;
     return S2MV_OK;

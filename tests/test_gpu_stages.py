@@ -102,7 +102,10 @@ def test_ca_cross_bit_exact(pipe, oracle, bud_sbs, H, W, D, zd):
 def test_ca_cross_other_arm_limits(pipe, oracle, bud_sbs):
     L, R = pair(oracle, bud_sbs, 60, 256, 4)
     cost, _ = oracle.ci_adcensus(L, R, 16, 8, 10.0, 30.0)
-    for ucd, lcd, usd, lsd in ((30.0, 10.0, 25, 12), (5.0, 2.0, 4, 2), (20.0, 6.0, 1, 0)):
+    # thresholds on both sides of 127 (packed-byte tests vs per-byte tests), fractional, negative, never failing
+    for ucd, lcd, usd, lsd in ((30.0, 10.0, 25, 12), (5.0, 2.0, 4, 2), (20.0, 6.0, 1, 0), (127.0, 0.0, 17, 9),
+                               (127.9, 126.5, 17, 9), (128.0, 6.0, 17, 9), (20.0, 200.0, 17, 9), (-1.0, 6.0, 17, 9),
+                               (20.0, -0.5, 17, 9), (255.0, 300.0, 17, 9), (0.0, 0.0, 17, 9), (20.0, 6.0, 17, 40)):
         arms, acost = pipe.ca_cross(L, cost, ucd, lcd, usd, lsd)
         oarms = oracle.cross_arms(L, ucd, lcd, usd, lsd)
         assert np.array_equal(arms, oarms)
