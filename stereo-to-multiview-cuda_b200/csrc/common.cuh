@@ -75,6 +75,35 @@ __device__ __forceinline__ void add2_rn(float &a0, float &a1, float v0, float v1
     asm("add.rn.f32x2 %0, %0, %1;" : "+l"(A) : "l"(V));
     asm("mov.b64 {%0,%1}, %2;" : "=f"(a0), "=f"(a1) : "l"(A));
 }
+// Two independent fp32 operations per lane in one issue slot (sm_100a f32x2 forms); each half rounds exactly
+// like the scalar __f*_rn.  A pair lives in a 64-bit register: low word = first element.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi)
+{
+    f32x2_t r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b)
+{
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b)
+{
+    f32x2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c)
+{
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 __device__ __forceinline__ void acc4(float4 &a, const float4 v)
 {
 #ifdef S2MV_NO_FADD2

@@ -215,6 +215,58 @@ k_dbm(const DbmArgs a)
     }
 }
 
+// Four horizontally adjacent pixels per thread, for W % 4 == 0 and 16-byte aligned planes (the launcher
+// checks): the masks and disparities arrive as float4 and the 12 output bytes leave as three aligned words, so
+// a warp writes 384 contiguous bytes instead of three interleaved runs of single bytes.  Per pixel the
+// arithmetic is k_dbm's.
+__global__ void __launch_bounds__(256)
+k_dbm4(const DbmArgs a)
+{
+    const int W4 = a.W >> 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= W4 * a.H) return;
+    const int ty = idx / W4, x0 = (idx - ty * W4) * 4;
+    const int vi = blockIdx.z;
+    const float shift = a.shift[vi], shift_r = (float)(1.0 - (double)shift);
+    const size_t row = (size_t)ty * a.W, i = row + x0;
+    const float4 mr4 = __ldg(reinterpret_cast<const float4 *>(a.maskR + i));
+    const float4 ml4 = __ldg(reinterpret_cast<const float4 *>(a.maskL + i));
+    const float4 tm4 = __ldg(reinterpret_cast<const float4 *>(a.tmask + i));
+    const float4 dr4 = __ldg(reinterpret_cast<const float4 *>(a.dispR + i));
+    const float4 dl4 = __ldg(reinterpret_cast<const float4 *>(a.dispL + i));
+    const float mrs[4] = {mr4.x, mr4.y, mr4.z, mr4.w}, mls[4] = {ml4.x, ml4.y, ml4.z, ml4.w};
+    const float tms[4] = {tm4.x, tm4.y, tm4.z, tm4.w};
+    const float drs[4] = {dr4.x, dr4.y, dr4.z, dr4.w}, dls[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
+    uint32_t pl[4], pr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float ftx = small_to_float((uint32_t)(x0 + j));
+        pl[j] = warp_fetch(a.pixL + row, drs[j], -shift, ftx, a.W);
+        pr[j] = warp_fetch(a.pixR + row, dls[j], shift_r, ftx, a.W);
+    }
+    uint32_t bytes[12];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float mr = fmaxf(mrs[j], 0.0f), ml = fmaxf(mls[j], 0.0f), m = fmaxf(tms[j], 0.0f);
+        const float im = fmaxf(__fsub_rn(1.0f, tms[j]), 0.0f);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float cl = __fsub_rn(__uint_as_float(__byte_perm(pl[j], 0x4b000000u, 0x7440 + c)), kTwo23);
+            const float cr = __fsub_rn(__uint_as_float(__byte_perm(pr[j], 0x4b000000u, 0x7440 + c)), kTwo23);
+            const float wl = small_to_float(trunc_bits(__fmul_rn(cl, mr)) & 0xffu);
+            const float wr = small_to_float(trunc_bits(__fmul_rn(cr, ml)) & 0xffu);
+            bytes[3 * j + c] = trunc_bits(__fmul_rn(im, wl)) + trunc_bits(__fmul_rn(m, wr));  // low byte is the result
+        }
+    }
+    uint32_t *o = reinterpret_cast<uint32_t *>(a.views + ((size_t)a.view_index[vi] * a.H * a.W + i) * 3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const uint32_t lo = __byte_perm(bytes[4 * k], bytes[4 * k + 1], 0x0040);      // b0 | b1 << 8
+        const uint32_t hi = __byte_perm(bytes[4 * k + 2], bytes[4 * k + 3], 0x0040);  // b2 | b3 << 8
+        o[k] = __byte_perm(lo, hi, 0x5410);
+    }
+}
+
 // mux_multiview_kernel_2 / mux_multiview_kernel (d_mux_multiview.cu:38-124)
 struct MuxArgs {
     const uint8_t *views[16];

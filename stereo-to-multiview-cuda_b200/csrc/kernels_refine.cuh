@@ -485,4 +485,92 @@ k_bilateral4(const float *__restrict__ in0, const float *__restrict__ in1, float
         if (gx + o < W) o4[o] = __fdiv_rn(res[o], norm[o]);
 }
 
+// k_bilateral4<R, true> with the per-tap arithmetic issued two outputs at a time (f32x2): the subtract, the
+// weight product, the norm add and the value FMA of outputs (0,1) and (2,3) pair up; only the colour-table
+// lookup stays per tap — 10 issue slots per two taps instead of 14.  A pair needs its two tile values in one
+// aligned 64-bit register: for even kx they are adjacent in the row as loaded (tile A), for odd kx in the same
+// row shifted by one (tile B, a second copy of the tile staged next to it).  The spatial weights are the same
+// for every thread: they arrive already duplicated into pairs as a kernel parameter and are read through the
+// constant path, which keeps them off the shared-memory pipe (the kernel's other ceiling: 60 table lookups
+// plus the row loads per 60 taps).  Every output accumulates ky-major, kx-minor with the same operations and
+// roundings as k_bilateral4.
+template <int R>
+struct BilPairs {
+    float2 w[2 * R + 1][(2 * R + 2) & ~1];   // (w, w) per tap, rows padded to an even count
+};
+
+template <int R>
+__global__ void __launch_bounds__(256, 2)
+k_bilateral4p(const float *__restrict__ in0, const float *__restrict__ in1, float *__restrict__ out0,
+              float *__restrict__ out1, const __grid_constant__ BilPairs<R> wpairs, const float *__restrict__ colour,
+              int ncolour, int H, int W)
+{
+    constexpr int KW = 2 * R + 1;
+    constexpr int TWP = (kBil4W + 2 * R + 3) & ~3, TH = kBil4H + 2 * R;
+    constexpr int NA = (4 + 2 * R + 3) / 4;                     // float4 loads of tile A per kernel row
+    constexpr int NB = (2 + 2 * R + 3) / 4;                     // and of tile B
+    static_assert(kBil4W - 4 + 4 * NA <= TWP, "row reads stay inside the padded tile");
+    extern __shared__ __align__(16) float bsm4[];
+    float *tileA = bsm4, *tileB = tileA + TWP * TH;
+    float *scol = tileB + TWP * TH;
+    const float *__restrict__ in = blockIdx.z ? in1 : in0;
+    float *__restrict__ out = blockIdx.z ? out1 : out0;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int bx = blockIdx.x * kBil4W, by = blockIdx.y * kBil4H;
+    for (int i = tid; i < TWP * TH; i += 256) {
+        const int ty = i / TWP, tx = i - ty * TWP;
+        const float *row = in + (size_t)clampi(by + ty - R, 0, H - 1) * W;
+        tileA[i] = row[clampi(bx + tx - R, 0, W - 1)];
+        tileB[i] = row[clampi(bx + tx + 1 - R, 0, W - 1)];
+    }
+    for (int i = tid; i < ncolour; i += 256) scol[i] = colour[i];
+    __syncthreads();
+    const int x0 = 4 * threadIdx.x, gx = bx + x0, gy = by + threadIdx.y;
+    if (gx >= W || gy >= H) return;
+    const float *centre = tileA + (threadIdx.y + R) * TWP + x0 + R;
+    const f32x2_t nva[2] = {pack2(-centre[0], -centre[1]), pack2(-centre[2], -centre[3])};
+    f32x2_t norm[2] = {pack2(0.0f, 0.0f), pack2(0.0f, 0.0f)}, res[2] = {norm[0], norm[0]};
+#pragma unroll 1
+    for (int ky = 0; ky < KW; ++ky) {
+        f32x2_t pa[2 * NA], pb[2 * NB];
+        const ulonglong2 *arow = reinterpret_cast<const ulonglong2 *>(tileA + (threadIdx.y + ky) * TWP + x0);
+        const ulonglong2 *brow = reinterpret_cast<const ulonglong2 *>(tileB + (threadIdx.y + ky) * TWP + x0);
+        const float2 *wrow = wpairs.w[ky];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const ulonglong2 t = arow[i];
+            pa[2 * i] = t.x; pa[2 * i + 1] = t.y;
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const ulonglong2 t = brow[i];
+            pb[2 * i] = t.x; pb[2 * i + 1] = t.y;
+        }
+#pragma unroll
+        for (int op = 0; op < 2; ++op) {        // outputs (0,1), then (2,3)
+#pragma unroll
+            for (int kx = 0; kx < KW; ++kx) {
+                // (v[2 op + kx], v[2 op + kx + 1]) of the row
+                const f32x2_t vs = (kx & 1) ? pb[op + (kx - 1) / 2] : pa[op + kx / 2];
+                float d0, d1;
+                unpack2(add2(vs, nva[op]), d0, d1);
+                const int c0 = __float_as_int(__fadd_rz(fabsf(d0), 2097152.0f)) & 0x7ffffc;
+                const int c1 = __float_as_int(__fadd_rz(fabsf(d1), 2097152.0f)) & 0x7ffffc;
+                const float s0 = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(scol) + c0);
+                const float s1 = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(scol) + c1);
+                const f32x2_t wt = mul2(pack2(wrow[kx].x, wrow[kx].y), pack2(s0, s1));
+                norm[op] = add2(norm[op], wt);
+                res[op] = fma2(vs, wt, res[op]);
+            }
+        }
+    }
+    float r[4], nm[4];
+    unpack2(res[0], r[0], r[1]); unpack2(res[1], r[2], r[3]);
+    unpack2(norm[0], nm[0], nm[1]); unpack2(norm[1], nm[2], nm[3]);
+    float *o4 = out + (size_t)gy * W + gx;
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+        if (gx + o < W) o4[o] = __fdiv_rn(r[o], nm[o]);
+}
+
 }  // namespace s2mv

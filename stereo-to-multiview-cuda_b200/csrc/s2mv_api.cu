@@ -261,6 +261,7 @@ struct s2mv_ctx {
     int irv_nbp = 0;
     float *bil_spatial = nullptr, *bil_colour = nullptr, *gauss_kernel = nullptr;
     std::vector<float> h_gauss_kernel;  // host copy of gauss_kernel (for its fp32 sum)
+    std::vector<float> h_bil_spatial;   // host copy of bil_spatial (passed to k_bilateral4p as a kernel parameter)
     uint8_t *occl[2] = {}, *occlB[2] = {};
     float *mask[2] = {}, *tmask = nullptr;
     uint8_t *views = nullptr, *interlaced = nullptr;
@@ -414,6 +415,7 @@ static int set_kernel_attrs()
     TRY(set_smem(k_bilateral, 160 * 1024));
     TRY(set_smem(k_bilateral4<7, true>, 64 * 1024));
     TRY(set_smem(k_bilateral4<7, false>, 64 * 1024));
+    TRY(set_smem(k_bilateral4p<7>, 96 * 1024));
     TRY(set_smem(k_gauss_dilate4<10>, 64 * 1024));
     TRY(set_smem(k_gauss_dilate, 160 * 1024));
     TRY(set_smem(k_irv_vote, 64 * 1024));
@@ -566,6 +568,7 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
         host_gaussian_kernel(k, p->bilateral_radius, p->bilateral_sigma_spatial);
         TRY(dev_alloc_t(c, &c->bil_spatial, k.size()));
         CU(cudaMemcpy(c->bil_spatial, k.data(), k.size() * sizeof(float), cudaMemcpyHostToDevice));
+        c->h_bil_spatial = k;
         host_gaussian_1d(k, p->num_disp, p->bilateral_sigma_color);
         TRY(dev_alloc_t(c, &c->bil_colour, k.size()));
         CU(cudaMemcpy(c->bil_colour, k.data(), k.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -912,17 +915,41 @@ static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2],
     return S2MV_OK;
 }
 
+// k_dbm4 when the planes allow vector access, k_dbm otherwise
+static void launch_dbm(const DbmArgs &d, int nviews, cudaStream_t st)
+{
+    auto al16 = [](const void *p) { return ((uintptr_t)p & 15) == 0; };
+    if (d.W % 4 == 0 && al16(d.dispL) && al16(d.dispR) && al16(d.maskL) && al16(d.maskR) && al16(d.tmask) &&
+        ((uintptr_t)d.views & 3) == 0) {
+        const long long threads = (long long)(d.W / 4) * d.H;
+        k_dbm4<<<dim3((unsigned)((threads + 255) / 256), 1, nviews), 256, 0, st>>>(d);
+    } else {
+        k_dbm<<<dim3((d.W + 255) / 256, d.H, nviews), 256, 0, st>>>(d);
+    }
+}
+
 // in/out per view slot (nviews = 1 or 2).  `bounded`: the inputs are this pipeline's own disparities
 // (|a - s| <= num_disp - 1), see k_bilateral4.
 static int launch_bilateral(s2mv_ctx *c, const float *const in[2], float *const out[2], int nviews,
                             const float *spatial, const float *colour, int radius, int ncolour, bool bounded, int H,
-                            int W, cudaStream_t st)
+                            int W, cudaStream_t st, const float *h_spatial = nullptr)
 {
     if (radius == 7 && (size_t)ncolour * sizeof(float) <= 32 * 1024) {
         constexpr int R = 7, KW = 15, KWP = 16, TWP = (kBil4W + 2 * R + 3) & ~3, TH = kBil4H + 2 * R;
         const size_t smem = ((size_t)TWP * TH + KWP * KW + ncolour) * sizeof(float);
         dim3 g((W + kBil4W - 1) / kBil4W, (H + kBil4H - 1) / kBil4H, nviews);
-        if (bounded)
+        static const bool packed = !(getenv("S2MV_BILATERAL_SCALAR") && atoi(getenv("S2MV_BILATERAL_SCALAR")));  // A/B hook
+        if (bounded && packed && h_spatial) {
+            const size_t smem2 = ((size_t)2 * TWP * TH + ncolour) * sizeof(float);
+            BilPairs<R> w2;
+            for (int ky = 0; ky < KW; ++ky)
+                for (int kx = 0; kx < KWP; ++kx) {
+                    const float w = kx < KW ? h_spatial[ky * KW + kx] : 0.0f;
+                    w2.w[ky][kx] = make_float2(w, w);
+                }
+            k_bilateral4p<R><<<g, dim3(32, 8), smem2, st>>>(in[0], in[nviews - 1], out[0], out[nviews - 1], w2, colour,
+                                                            ncolour, H, W);
+        } else if (bounded)
             k_bilateral4<R, true><<<g, dim3(32, 8), smem, st>>>(in[0], in[nviews - 1], out[0], out[nviews - 1], spatial,
                                                                  colour, ncolour, H, W);
         else
@@ -1042,7 +1069,7 @@ static int run_refine(s2mv_ctx *c, float *fl, float *fr, cudaStream_t st)
         const float *bin[2] = {c->disp[0], c->disp[1]};
         float *bout[2] = {fl, fr};
         TRY(launch_bilateral(c, bin, bout, 2, c->bil_spatial, c->bil_colour, p.bilateral_radius, p.num_disp, true, H, W,
-                             st));
+                             st, c->h_bil_spatial.data()));
     }
     return S2MV_OK;
 }
@@ -1076,7 +1103,7 @@ static int run_dibr(s2mv_ctx *c, const float *fl, const float *fr, uint8_t *d_in
             d.shift[v - 1] = (float)(1.0 - ((1.0 * (double)(float)v) / ((double)(float)V - 1.0)));
             d.view_index[v - 1] = v;
         }
-        k_dbm<<<dim3((W + 255) / 256, H, V - 2), 256, 0, st>>>(d);
+        launch_dbm(d, V - 2, st);
         KCHECK();
         c->launches += 1;
     }

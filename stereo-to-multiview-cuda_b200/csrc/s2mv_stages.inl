@@ -452,7 +452,7 @@ extern "C" int s2mv_dibr_dbm(s2mv_ctx *ctx, uint8_t *img_out, const uint8_t *img
     d.pixL = c->pix[0]; d.pixR = c->pix[1]; d.dispL = c->dispF[0]; d.dispR = c->dispF[1];
     d.maskL = c->mask[0]; d.maskR = c->mask[1]; d.tmask = c->tmask; d.views = c->views; d.H = H; d.W = W;
     d.shift[0] = shift; d.view_index[0] = 0;
-    k_dbm<<<dim3((W + 255) / 256, H, 1), 256, 0, st>>>(d);
+    launch_dbm(d, 1, st);
     KCHECK();
     TRY(download(img_out, c->views, n * 3, st));
     CU(cudaStreamSynchronize(st));
