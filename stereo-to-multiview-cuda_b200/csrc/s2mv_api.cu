@@ -938,7 +938,8 @@ static int launch_bilateral(s2mv_ctx *c, const float *const in[2], float *const 
         constexpr int R = 7, KW = 15, KWP = 16, TWP = (kBil4W + 2 * R + 3) & ~3, TH = kBil4H + 2 * R;
         const size_t smem = ((size_t)TWP * TH + KWP * KW + ncolour) * sizeof(float);
         dim3 g((W + kBil4W - 1) / kBil4W, (H + kBil4H - 1) / kBil4H, nviews);
-        static const bool packed = !(getenv("S2MV_BILATERAL_SCALAR") && atoi(getenv("S2MV_BILATERAL_SCALAR")));  // A/B hook
+        const char *sc = getenv("S2MV_BILATERAL_SCALAR");  // test / A-B hook: 1 = the one-output-at-a-time kernel
+        const bool packed = !(sc && atoi(sc));
         if (bounded && packed && h_spatial) {
             const size_t smem2 = ((size_t)2 * TWP * TH + ncolour) * sizeof(float);
             BilPairs<R> w2;

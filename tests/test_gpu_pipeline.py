@@ -237,6 +237,16 @@ def test_region_voting_dense_and_sparse_paths_agree_with_oracle(s2mv, oracle, bu
         assert_frame_equal(got, want)
 
 
+def test_bilateral_scalar_kernel_agrees_with_oracle(s2mv, oracle, bud_sbs, monkeypatch):
+    # the frame call runs the paired (f32x2) bilateral kernel; the one-output-at-a-time kernel it replaced stays
+    # selectable and is held to the same bar on the same frame
+    monkeypatch.setenv("S2MV_BILATERAL_SCALAR", "1")
+    sbs = np.ascontiguousarray(np.concatenate([bud_sbs[100:228, :320], bud_sbs[100:228, 640:960]], 1))
+    with s2mv.Pipeline(0) as p:
+        got, want = run_both(p, oracle, sbs, 320, 96, 40)
+        assert_frame_equal(got, want)
+
+
 def test_host_registration_of_pageable_buffers(s2mv):
     # pageable numpy buffers: staged by default, page-locked in place with host registration on; the same
     # bytes either way, repeated calls reuse the registration, switching it off releases everything
