@@ -51,19 +51,6 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__device__ __forceinline__ float4 ld_stream4(const float4 *p)
-{
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void st_stream4(float4 *p, float4 v)
-{
-    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
-                 "f"(v.w) : "memory");
-}
-
 // Exact-order accumulate: plain IEEE adds, never contracted.  sm_100a's packed add (FADD2: two
 // independent round-to-nearest fp32 adds per lane, one issue slot) halves the issue cost of the
 // aggregation loops, whose ceiling is instruction issue, not the FP32 pipe (tools/ubench_fadd2.cu).
