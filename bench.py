@@ -23,17 +23,26 @@ parameters.  With N GPUs every rank processes its own K frames of the stream
           s2mv_stream_collect, 3 frames in flight: copies overlap kernels), with
           the synchronous adcensus_stm-contract call (s2mv_process_sbs) reported
           beside it as e2e.synchronous_call.
-  roofline  for the slowest cost-volume kernel: algorithmic bytes per launch
-          (stage-separable model of BASELINE.md §3: 40 B per disparity
-          evaluation = 20 V per frame, split 6 V / 4 V / 4 V / 6 V over the four
-          kernels) / its mean duration from CUDA events inside the timed steps,
-          against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  roofline  for the slowest cost-volume kernel: the bytes its algorithm must
+          move per launch (2V / 4V / 4V / 2V for the four fused kernels; ncu's
+          DRAM bytes agree to ~1 %) / its mean duration from CUDA events inside
+          the timed steps, against the measured HBM copy bandwidth in
+          MEASURED_PEAKS.json; `bound` from the ncu capture (hbm | issue); all
+          four kernels under roofline.kernels; the stage-separable 40 B/DE
+          model only as a separately named throughput.
   cpu_baseline  the CPU oracle (C restatement of the reference kernels, OpenMP
-          over all host cores) on a bounded sample of the same frame.
+          over all host cores) on one whole frame.
+
+  extra   other workloads through the same code (never the headline): config3
+          (synthetic stream frame, half of the pixels fail the cross-check),
+          bud_1080p (a non-degenerate bundled pair -- fish_1/fish_2 are
+          byte-identical images); reference_gpu = the reference's OWN kernels
+          timed on this box (oracle/ref_gpu_time.py, separate process); with
+          N > 1: rowband = one 3840x2160 D=256 frame in N row bands.
 
 --impl reference: the reference is CUDA-only; its CPU form is the same C
-restatement (oracle/), timed on all host cores, each step a bounded sample
-(a row band of the frame, extrapolated to a frame — stated in `sample`).
+restatement (oracle/), timed on all host cores, one WHOLE frame per step, same
+`config` as the main arm.
 """
 import argparse
 import json
@@ -123,20 +132,37 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_sample(sbs, threads_note=True):
-    """Oracle, all host cores, on a BAND_ROWS-row band of the frame (full pipeline)."""
+def config_dict(workload, world):
+    """`config` of the JSON line -- the SAME dict for the main arm and for --impl reference."""
+    return {"workload": workload, "parallelism": f"frame-parallel x{world}, no collectives",
+            "l2": "256 MB flush write between timed steps; per-frame volume traffic >> L2"}
+
+
+def cpu_frame(sbs):
+    """The CPU oracle (C restatement of the reference kernels, OpenMP over all host cores) on ONE WHOLE frame:
+    seconds, threads used."""
+    import oracle_py
+    t0 = time.perf_counter()
+    oracle_py.adcensus_stm(sbs, W, H, W, num_views=V, angle=18, D=D, zd=ZD, **ALGO)
+    return time.perf_counter() - t0, oracle_py.max_threads()
+
+
+def cpu_band_x8(sbs):
+    """Round 1's bounded sample (a BAND_ROWS-row band, x8), kept only as a cross-check of the whole-frame time."""
     import oracle_py
     y0 = (H - BAND_ROWS) // 2
     band = np.ascontiguousarray(sbs[y0:y0 + BAND_ROWS])
     t0 = time.perf_counter()
     oracle_py.adcensus_stm(band, W, BAND_ROWS, W, num_views=V, angle=18, D=D, zd=ZD, **ALGO)
-    dt = time.perf_counter() - t0
-    return dt, oracle_py.max_threads(), (f"rows {y0}..{y0 + BAND_ROWS} of the frame ({W}x{BAND_ROWS}, 1/{H // BAND_ROWS} "
-                                         f"frame), full pipeline, extrapolated x{H // BAND_ROWS}")
+    return (time.perf_counter() - t0) * (H // BAND_ROWS)
+
+
+CPU_SAMPLE = "one whole 1920x1080 frame per step, full pipeline (disparities + 8-view interlaced frame), nothing extrapolated"
 
 
 def run_reference_arm(args):
-    """The reference is CUDA-only: its CPU implementation is the C restatement under oracle/."""
+    """The reference is CUDA-only: its CPU implementation is the C restatement under oracle/, all host cores,
+    one WHOLE frame of the main arm's workload per step (same `config`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -146,26 +172,226 @@ def run_reference_arm(args):
     import oracle_py
     oracle_py.build()
     frames, workload = load_frames(args.workload)
-    sbs = frames[0]
-    for _ in range(args.warmup):
-        cpu_sample(sbs)
-    t = 0.0
-    sample = cores = None
-    for _ in range(args.steps):
-        dt, cores, sample = cpu_sample(sbs)
+    for i in range(args.warmup):
+        cpu_frame(frames[i % len(frames)])
+    t, cores = 0.0, None
+    for i in range(args.steps):
+        dt, cores = cpu_frame(frames[i % len(frames)])
         t += dt
-    per_frame = (t / args.steps) * (H // BAND_ROWS)
-    fps = 1.0 / per_frame
+    fps = args.steps / t
+    band = cpu_band_x8(frames[0])
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "bundled fish pair, upscaled (synthetic size)",
-        "config": {"workload": workload, "step": sample},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": DATA[args.workload],
+        "config": config_dict(workload, args.gpus),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": CPU_SAMPLE,
+                         "band_x8_estimate_frames_per_s": 1.0 / band},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
     return 0
+
+
+DATA = {"config2": "bundled fish pair upscaled to 1080p (no published dataset for this path)",
+        "config3": "synthetic stereo stream (no published dataset for this path)"}
+KERNEL_NAMES = {"ci_h1": "k_line<LM_CI_H> (cost init + H pass 1)", "v2": "k_line<LM_V> (V pass 2)",
+                "v3": "k_line<LM_V> (V pass 3)", "h4_wta": "k_line<LM_H_WTA> (H pass 4 + WTA)"}
+
+
+class Rig:
+    """One context + device/pinned buffers for 1080p D=128 frames; the three ways a frame is timed."""
+
+    def __init__(self, torch, s2mv_b200, sharding, local_rank):
+        self.torch, self.sharding = torch, sharding
+        self.dev = torch.device("cuda", local_rank)
+        self.pipe = s2mv_b200.Pipeline(local_rank, num_rows=H, num_cols=W, num_disp=D, zero_disp=ZD, num_views=V, angle=18, **ALGO)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.d_dl = torch.empty((H, W), dtype=torch.float32, device=self.dev)
+        self.d_dr = torch.empty_like(self.d_dl)
+        self.d_out = torch.empty((H, W, 3), dtype=torch.uint8, device=self.dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)   # > 126 MB L2
+        self.h_dl = torch.empty((H, W), dtype=torch.float32).pin_memory()
+        self.h_dr = torch.empty((H, W), dtype=torch.float32).pin_memory()
+        self.h_out = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+
+    def device_resident(self, frames, K, Wm):
+        """frames/s with the inputs already in HBM: CUDA events around s2mv_process_sbs_device."""
+        torch, pipe, sharding = self.torch, self.pipe, self.sharding
+        d_frames = [torch.from_numpy(f).to(self.dev) for f in frames]
+        NF = len(d_frames)
+
+        def step(i):
+            pipe.process_device(d_frames[i % NF].data_ptr(), 2 * W, self.d_dl.data_ptr(), self.d_dr.data_ptr(),
+                                self.d_out.data_ptr(), self.stream)
+
+        for i in range(Wm):
+            step(i)
+        torch.cuda.synchronize()
+        pipe.enable_timing(True)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        stage_ms = {k: 0.0 for k in ("prepare", "costvol", "refine", "dibr")}
+        kern_ms = {k: 0.0 for k in ("ci_h1", "v2", "v3", "h4_wta")}
+        sharding.barrier()
+        torch.cuda.synchronize()
+        launches = 0
+        for i in range(K):
+            self.flush.fill_(i & 0xff)                 # L2 flush between timed iterations (not timed)
+            ev[i][0].record()
+            step(i)
+            ev[i][1].record()
+            ev[i][1].synchronize()
+            for k, v in pipe.last_timings().items():
+                stage_ms[k] += v
+            for k, v in pipe.last_costvol_kernel_timings().items():
+                kern_ms[k] += v
+            launches += pipe.last_launch_count
+        torch.cuda.synchronize()
+        sharding.barrier()
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        pipe.enable_timing(False)
+        fps, _, slowest_s = sharding.aggregate_throughput(K, dev_ms / 1e3, self.dev)
+        return {"fps": fps, "ms_per_step": 1e3 * slowest_s / K, "launches": launches,
+                "stage_ms": {k: v / K for k, v in stage_ms.items()}, "kern_ms": {k: v / K for k, v in kern_ms.items()},
+                "last_out": self.d_out.cpu().numpy()}
+
+    def synchronous(self, np_ins, outs, K, Wm):
+        """frames/s through s2mv_process_sbs (the adcensus_stm contract: returns after the D2H copies)."""
+        pipe, sharding = self.pipe, self.sharding
+        NF = len(np_ins)
+        for i in range(Wm):
+            pipe.adcensus_stm_into(np_ins[i % NF], *outs)
+        sharding.barrier()
+        self.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            pipe.adcensus_stm_into(np_ins[i % NF], *outs)
+        self.torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        sharding.barrier()
+        return sharding.aggregate_throughput(K, dt, self.dev)[0]
+
+    def streamed(self, np_ins, K, Wm, depth=3):
+        """frames/s through the asynchronous frame stream (the video loop): every frame host frame -> the slot's
+        pinned buffer -> H2D -> all kernels -> D2H of both disparity maps and the interlaced frame into pinned
+        host memory; copies of neighbouring frames overlap the kernels."""
+        pipe, sharding = self.pipe, self.sharding
+        NF = len(np_ins)
+        pipe.stream_open(depth)
+
+        def run(n):
+            got = None
+            for i in range(n):
+                if pipe.stream_pending == depth:
+                    got = pipe.stream_collect(copy=False)
+                np.copyto(pipe.stream_input_buffer(), np_ins[i % NF])   # stands in for the decoder writing the frame
+                pipe.stream_submit(None)
+            while pipe.stream_pending:
+                got = pipe.stream_collect(copy=False)
+            return got
+
+        run(Wm)
+        sharding.barrier()
+        self.torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got = run(K)
+        dt = time.perf_counter() - t0
+        sharding.barrier()
+        got = tuple(np.array(g) for g in got)
+        pipe.stream_close()
+        return sharding.aggregate_throughput(K, dt, self.dev)[0], got
+
+
+def roofline_record(kern_ms, stage_ms):
+    """Per-kernel roofline of the four cost-volume kernels + the record of the slowest one.
+
+    `achieved` = the bytes the kernel's algorithm MUST move per launch (compulsory traffic of the fused pipeline:
+    pass 1 only writes the volume, passes 2/3 read and write it, pass 4 only reads it: 2V/4V/4V/2V, V = one view's
+    volume; both views per launch) / its mean duration inside the timed steps.  ncu's DRAM bytes for the same
+    kernels (profiles/ncu_traffic.json, `traffic`) agree with that figure to ~1 %, so `frac` is also the
+    fraction of the measured HBM copy bandwidth the kernel really sustains.  `bound` comes from the ncu
+    capture: "hbm" when the DRAM pipe is the busiest unit, "issue" when the instruction issue slots are.
+    The stage-separable model of SURVEY §8(d) (40 B per disparity evaluation = 20V per frame: what the same
+    passes would move unfused) is reported separately under `model_40B_per_de` and never called a fraction
+    of anything the hardware did."""
+    Vb = W * H * D * 4
+    comp = {"ci_h1": 2 * Vb, "v2": 4 * Vb, "v3": 4 * Vb, "h4_wta": 2 * Vb}
+    model = {"ci_h1": 6 * Vb, "v2": 4 * Vb, "v3": 4 * Vb, "h4_wta": 6 * Vb}
+    peak, peak_src = measured_peak()
+    ncu = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            ncu = json.load(f)
+    except Exception:
+        pass
+    kernels = {}
+    for k, ms in kern_ms.items():
+        n = ncu.get(k, {})
+        traffic = n.get("dram_bytes_per_launch")
+        issue, dram = n.get("issue_active_pct"), n.get("dram_throughput_pct")
+        bound = None if issue is None or dram is None else ("hbm" if dram >= issue else "issue")
+        kernels[k] = {"kernel": KERNEL_NAMES[k], "ms_per_launch": ms, "compulsory_bytes_per_launch": comp[k],
+                      "achieved_gbs": comp[k] / (ms * 1e-3) / 1e9, "frac": comp[k] / (ms * 1e-3) / 1e9 / peak,
+                      "traffic": traffic,
+                      "actual_dram_gbs": None if traffic is None else traffic / (ms * 1e-3) / 1e9,
+                      "actual_dram_frac": None if traffic is None else traffic / (ms * 1e-3) / 1e9 / peak,
+                      "ncu_issue_active_pct": issue, "ncu_dram_throughput_pct": dram, "bound": bound}
+    dom = max(kern_ms, key=kern_ms.get)
+    kd = kernels[dom]
+    total_ms = sum(kern_ms.values())
+    costvol_ms = stage_ms["prepare"] + stage_ms["costvol"]
+    de = 2.0 * W * H * D
+    return {"bound": kd["bound"] or "hbm", "kernel": kd["kernel"], "achieved": kd["achieved_gbs"], "peak": peak,
+            "unit": "GB/s", "frac": kd["frac"], "traffic": kd["traffic"], "actual_dram_frac": kd["actual_dram_frac"],
+            "peak_source": peak_src, "algorithmic_bytes_per_launch": comp[dom], "ms_per_launch": kd["ms_per_launch"],
+            "kernels": kernels,
+            "costvol_four_kernels": {"ms": total_ms, "compulsory_bytes": sum(comp.values()),
+                                     "achieved_gbs": sum(comp.values()) / (total_ms * 1e-3) / 1e9,
+                                     "frac": sum(comp.values()) / (total_ms * 1e-3) / 1e9 / peak},
+            "model_40B_per_de": {"note": "stage-separable model (SURVEY 8d): 20V per frame as if no stage were fused; "
+                                         "a throughput expressed in bytes, not traffic",
+                                 "bytes_per_launch": model[dom], "costvol_leg_ms": costvol_ms,
+                                 "mde_per_s": de / (costvol_ms * 1e-3) / 1e6,
+                                 "equivalent_gbs": 40.0 * de / (costvol_ms * 1e-3) / 1e9,
+                                 "equivalent_over_peak": 40.0 * de / (costvol_ms * 1e-3) / 1e9 / peak}}
+
+
+def reference_gpu_record():
+    """The reference's own CUDA kernels on this box (oracle/_ref, built from /root/reference by oracle/build_ref.sh),
+    timed by oracle/ref_gpu_time.py in a separate process: a reported baseline, never on the product path."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "ref_gpu_time.py")], capture_output=True,
+                           text=True, timeout=600)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not line:
+            return {"unavailable": (r.stderr or r.stdout).strip().splitlines()[-1:] or ["no output"]}
+        return json.loads(line[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)}
+
+
+def rowband_record(steps, warmup):
+    """N > 1: BASELINE config 4 (one 3840x2160 D=256 frame in N row bands, halo rows over NVLink) -- the
+    multi-GPU mode with communication on the data path -- next to the frame-parallel number."""
+    import types
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import rowband_bench
+    a = types.SimpleNamespace(height=2160, width=3840, disp=256, seed=4000, steps=steps, warmup=warmup, check=True,
+                              baseline=True, transport="p2p", sha=False, single=False)
+    try:
+        res = rowband_bench.measure(a)
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)}
+    if res is None:
+        return None
+    chk = res.get("check", {})
+    return {"workload": res["workload"], "ms_per_frame": res["ms_per_frame"],
+            "single_context_ms": res.get("single_context_ms_per_frame"),
+            "speedup_vs_single_context": res.get("speedup_vs_single_context"),
+            "bit_exact": bool(chk) and all(chk.values()), "check": chk,
+            "phase_ms": res["phase_ms_max_over_ranks"], "transport": res["transport"],
+            "band_rows": res["band_rows"], "sub_image_rows": res["sub_image_rows"], "halo_rows": res["halo_rows"],
+            "arena_gb_per_gpu": res["arena_gb_per_gpu"], "steps": res["steps"]}
 
 
 def main():
@@ -175,6 +401,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip extra.* (other workloads, reference GPU timing, row bands)")
     ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
                     help="config2 (default, the headline): the bundled pair at 1080p; config3: synthetic 1080p stream")
     args = ap.parse_args()
@@ -187,177 +414,107 @@ def main():
         os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import s2mv_b200
-    from s2mv_b200_pkg import sharding
+    from s2mv_b200_pkg import sharding, synth
 
     rank, world, local_rank = sharding.dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
     sharding.init_process_group("nccl")
     K, Wm = args.steps, max(args.warmup, 3)
 
     frames, workload = load_frames(args.workload, rank)
     sbs = frames[0]
-    NF = len(frames)
-    pipe = s2mv_b200.Pipeline(local_rank, num_rows=H, num_cols=W, num_disp=D, zero_disp=ZD, num_views=V, angle=18, **ALGO)
-    stream = torch.cuda.current_stream().cuda_stream
-    d_frames = [torch.from_numpy(f).to(dev) for f in frames]
-    d_dl = torch.empty((H, W), dtype=torch.float32, device=dev)
-    d_dr = torch.empty_like(d_dl)
-    d_out = torch.empty((H, W, 3), dtype=torch.uint8, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-
-    def step_device(i=0):
-        pipe.process_device(d_frames[i % NF].data_ptr(), 2 * W, d_dl.data_ptr(), d_dr.data_ptr(), d_out.data_ptr(), stream)
-
-    # ---- device-resident throughput ------------------------------------
-    for _ in range(Wm):
-        step_device()
-    torch.cuda.synchronize()
-    pipe.enable_timing(True)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    stage_ms = {k: 0.0 for k in ("prepare", "costvol", "refine", "dibr")}
-    kern_ms = {k: 0.0 for k in ("ci_h1", "v2", "v3", "h4_wta")}
+    rig = Rig(torch, s2mv_b200, sharding, local_rank)
+    pipe = rig.pipe
     sampler = ClockSampler(local_rank)
-    sharding.barrier()
-    torch.cuda.synchronize()
     sampler.start()
-    launches = 0
-    for i in range(K):
-        flush.fill_(i & 0xff)                      # L2 flush between timed iterations (not timed)
-        ev[i][0].record()
-        step_device(i)
-        ev[i][1].record()
-        ev[i][1].synchronize()
-        for k, v in pipe.last_timings().items():
-            stage_ms[k] += v
-        for k, v in pipe.last_costvol_kernel_timings().items():
-            kern_ms[k] += v
-        launches += pipe.last_launch_count
-    torch.cuda.synchronize()
-    sharding.barrier()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    pipe.enable_timing(False)
-    fps, total_frames, slowest_s = sharding.aggregate_throughput(K, dev_ms / 1e3, dev)
 
-    # ---- end to end through the host-buffer C-ABI call -------------------
+    # ---- device-resident throughput (the `value`) -------------------------
+    dres = rig.device_resident(frames, K, Wm)
+
+    # ---- end to end through the host-buffer C-ABI call --------------------
     h_frames = [torch.from_numpy(f).pin_memory() for f in frames]
-    h_dl = torch.empty((H, W), dtype=torch.float32).pin_memory()
-    h_dr = torch.empty((H, W), dtype=torch.float32).pin_memory()
-    h_out = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
-    np_ins, np_dl, np_dr, np_out = [h.numpy() for h in h_frames], h_dl.numpy(), h_dr.numpy(), h_out.numpy()
-    for _ in range(Wm):
-        pipe.adcensus_stm_into(np_ins[0], np_dl, np_dr, np_out)
-    sharding.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(K):
-        pipe.adcensus_stm_into(np_ins[i % NF], np_dl, np_dr, np_out)   # synchronous: returns after the D2H copies
-    torch.cuda.synchronize()
-    e2e_sync_s = time.perf_counter() - t0
-    sharding.barrier()
-    e2e_sync_fps, _, _ = sharding.aggregate_throughput(K, e2e_sync_s, dev)
-    assert np.array_equal(np_out, d_out.cpu().numpy()), "host and device entry points disagree"
+    np_ins = [h.numpy() for h in h_frames]
+    np_dl, np_dr, np_out = rig.h_dl.numpy(), rig.h_dr.numpy(), rig.h_out.numpy()
+    e2e_sync_fps = rig.synchronous(np_ins, (np_dl, np_dr, np_out), K, Wm)
+    ref_out = np.array(np_out)
+    if len(frames) == 1:
+        assert np.array_equal(ref_out, dres["last_out"]), "host and device entry points disagree"
 
     # ---- the same call with PAGEABLE caller buffers (what an unchanged video_io.cpp passes) ----
     pg_in = [np.array(f) for f in frames]
-    pg_dl, pg_dr, pg_out = np.empty((H, W), np.float32), np.empty((H, W), np.float32), np.empty((H, W, 3), np.uint8)
+    pg = (np.empty((H, W), np.float32), np.empty((H, W), np.float32), np.empty((H, W, 3), np.uint8))
     pageable = {}
-    for mode in ("staged", "registered"):
-        pipe.set_host_registration(mode == "registered")
-        for _ in range(Wm):
-            pipe.adcensus_stm_into(pg_in[0], pg_dl, pg_dr, pg_out)
-        sharding.barrier()
-        t0 = time.perf_counter()
-        for i in range(K):
-            pipe.adcensus_stm_into(pg_in[i % NF], pg_dl, pg_dr, pg_out)
-        dt = time.perf_counter() - t0
-        pageable[mode] = sharding.aggregate_throughput(K, dt, dev)[0]
-        assert np.array_equal(pg_out, np_out)
-    pipe.set_host_registration(False)
+    for mode, m in (("default", 2), ("staged", 0), ("registered", 1)):   # default = what the adcensus_stm shim runs
+        pipe.set_host_registration(m)
+        pageable[mode] = rig.synchronous(pg_in, pg, K, Wm)
+        assert np.array_equal(pg[2], ref_out)
+    pipe.set_host_registration(0)
 
     # ---- end to end through the asynchronous frame stream (the video loop) ----
-    # every frame: host frame -> the slot's pinned buffer -> H2D -> all kernels -> D2H of both disparity
-    # maps and the interlaced frame into pinned host memory; copies of neighbouring frames overlap the kernels
     DEPTH = 3
-    pipe.stream_open(DEPTH)
-
-    def stream_run(n):
-        got = None
-        for i in range(n):
-            if pipe.stream_pending == DEPTH:
-                got = pipe.stream_collect(copy=False)
-            np.copyto(pipe.stream_input_buffer(), np_ins[i % NF])   # stands in for the decoder writing the frame
-            pipe.stream_submit(None)
-        while pipe.stream_pending:
-            got = pipe.stream_collect(copy=False)
-        return got
-
-    stream_run(Wm)
-    sharding.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    got = stream_run(K)
-    e2e_s = time.perf_counter() - t0
-    sharding.barrier()
+    e2e_fps, got = rig.streamed(np_ins, K, Wm, DEPTH)
     clocks = sampler.stop()
-    e2e_fps, _, _ = sharding.aggregate_throughput(K, e2e_s, dev)
-    assert np.array_equal(got[2], np_out) and np.array_equal(got[0], np_dl), "stream and synchronous entry points disagree"
-    pipe.stream_close()
+    assert np.array_equal(got[2], ref_out) and np.array_equal(got[0], np_dl), "stream and synchronous entry points disagree"
+
+    # ---- other workloads, same code, fewer steps (reported under `extra`, never the headline) ----
+    extra = {}
+    if not args.no_extras and world == 1:
+        Ke = max(3, min(K, 10))
+        others = {}
+        if args.workload != "config3":
+            others["config3"] = (load_frames("config3", rank)[0], WORKLOAD3)
+        bud = np.load(os.path.join(ROOT, "tests", "golden", "bud_2_3.npz"))["sbs"]
+        others["bud_1080p"] = ([np.ascontiguousarray(np.concatenate(
+            [synth.upscale_bilinear(bud[:, :640], H, W), synth.upscale_bilinear(bud[:, 640:], H, W)], axis=1))],
+            "img/bud_2+bud_3 bilinear-upscaled to 1920x1080 (a NON-degenerate bundled pair), D=128, zd=64, 8 views")
+        for name, (fr, wl) in others.items():
+            r = rig.device_resident(fr, Ke, 3)
+            pin = [torch.from_numpy(f).pin_memory() for f in fr]
+            e, _ = rig.streamed([h.numpy() for h in pin], Ke, 3, DEPTH)
+            extra[name] = {"workload": wl, "value": r["fps"], "e2e": e, "unit": "frames/s", "steps": Ke,
+                           "stage_ms": r["stage_ms"], "costvol_kernel_ms": r["kern_ms"]}
+    pipe.close()
+    if not args.no_extras and world > 1:
+        rb = rowband_record(5, 2)
+        if rb is not None:
+            extra["rowband"] = rb
 
     if rank != 0:
         return 0
 
-    # ---- roofline of the slowest cost-volume kernel ----------------------
-    Vbytes = W * H * D * 4                                # one view's cost volume
-    alg = {"ci_h1": 6 * Vbytes, "v2": 4 * Vbytes, "v3": 4 * Vbytes, "h4_wta": 6 * Vbytes}
-    dom = max(kern_ms, key=kern_ms.get)
-    dom_ms = kern_ms[dom] / K
-    peak, peak_src = measured_peak()
-    achieved = alg[dom] / (dom_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    costvol_ms = (stage_ms["prepare"] + stage_ms["costvol"]) / K
-    de = 2.0 * W * H * D
-    roofline = {"bound": "hbm", "kernel": {"ci_h1": "k_line<LM_CI_H> (cost init + H pass 1)", "v2": "k_line<LM_V> (V pass 2)",
-                                           "v3": "k_line<LM_V> (V pass 3)", "h4_wta": "k_line<LM_H_WTA> (H pass 4 + WTA)"}[dom],
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": dom_ms,
-                "costvol_leg": {"ms": costvol_ms, "mde_per_s": de / (costvol_ms * 1e-3) / 1e6,
-                                "achieved_gbs_40B_per_de": 40.0 * de / (costvol_ms * 1e-3) / 1e9,
-                                "frac": 40.0 * de / (costvol_ms * 1e-3) / 1e9 / peak}}
-
+    roofline = roofline_record(dres["kern_ms"], dres["stage_ms"])
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        dt, cores, sample = cpu_sample(sbs)
-        cpu = {"value": 1.0 / (dt * (H // BAND_ROWS)), "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": sample}
+        cpu_frame(sbs)                                    # warm (page-in, thread pool)
+        dt, cores = cpu_frame(sbs)
+        cpu = {"value": 1.0 / dt, "unit": "frames/s", "cores": cores, "kind": "port", "sample": CPU_SAMPLE,
+               "band_x8_estimate_frames_per_s": 1.0 / cpu_band_x8(sbs)}
+    if not args.no_extras and world == 1:
+        extra["reference_gpu"] = reference_gpu_record()
 
     print(json.dumps({
-        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": 1e3 * slowest_s / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": ("bundled fish pair upscaled to 1080p (no published dataset for this path)"
-                                 if args.workload == "config2" else "synthetic stereo stream (no published dataset for this path)"),
-        "config": {"workload": workload, "parallelism": f"frame-parallel x{world}, no collectives",
-                   "l2": "256 MB flush write between timed steps; per-frame volume traffic >> L2"},
+        "metric": METRIC, "value": dres["fps"], "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": dres["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": DATA[args.workload],
+        "config": config_dict(workload, world),
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": int(sbs.nbytes),
                 "d2h_bytes_per_step": int(np_dl.nbytes + np_dr.nbytes + np_out.nbytes),
                 "api": f"s2mv_stream_submit/collect, {DEPTH} frames in flight (host frame -> pinned slot -> H2D -> kernels -> D2H)",
-                "synchronous_call": {"value": e2e_sync_fps, "unit": "frames/s", "api": "s2mv_process_sbs (adcensus_stm contract)",
-                                     "pageable_caller_buffers": {"staged_through_pinned": pageable["staged"],
+                "synchronous_call": {"value": e2e_sync_fps, "unit": "frames/s", "api": "s2mv_process_sbs (adcensus_stm contract), pinned caller buffers",
+                                     "pageable_caller_buffers": {"shim_default_auto_page_lock": pageable["default"],
+                                                                 "staged_through_pinned": pageable["staged"],
                                                                  "page_locked_in_place": pageable["registered"],
                                                                  "unit": "frames/s"}}},
-        "gpu_launches": launches,
+        "gpu_launches": dres["launches"],
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "stage_ms": {k: v / K for k, v in stage_ms.items()},
-        "costvol_kernel_ms": {k: v / K for k, v in kern_ms.items()},
+        "reference_gpu": extra.get("reference_gpu"),
+        "stage_ms": dres["stage_ms"],
+        "costvol_kernel_ms": dres["kern_ms"],
+        "extra": extra,
     }))
     return 0
 

@@ -12,7 +12,30 @@
 // view_<k>.bmp, interlaced.bmp.
 #include <stdlib.h>
 
+#ifdef S2MV_REFERENCE_HEADERS
+// Boundary proof (oracle/build_ref.sh -> oracle/_ref/s2mv_image_refhdr): this same file compiled against the
+// REFERENCE's own headers -- the include list of image_io.cpp:10-26, OpenCV satisfied by empty stubs -- and
+// linked against libs2mv.so.  If a prototype here differed from the reference's, this would not link.
+#include "cuda_utils.h"
+#include "d_filter_gaussian.h"
+#include "d_filter.h"
+#include "d_filter_bilateral.h"
+#include "d_dibr_occl.h"
+#include "d_dibr_fwarp.h"
+#include "d_dibr_bwarp.h"
+#include "d_dc_wta.h"
+#include "d_dc_hslo.h"
+#include "d_dr_dcc.h"
+#include "d_dr_irv.h"
+#include "d_ca_cross.h"
+#include "d_ci_adcensus.h"
+#include "d_ci_census.h"
+#include "d_ci_ad.h"
+#include "d_tx_scale.h"
+#include "d_mux_multiview.h"
+#else
 #include "../include/s2mv_compat.h"
+#endif
 #include "bmp_io.h"
 
 static std::string image_path(const char *arg)

@@ -14,7 +14,14 @@
 #include <stdlib.h>
 #include <time.h>
 
+#ifdef S2MV_REFERENCE_HEADERS
+// Boundary proof (oracle/build_ref.sh -> oracle/_ref/s2mv_video_refhdr): this same file compiled against the
+// REFERENCE's own d_io.h (video_io.cpp:11-14; OpenCV satisfied by empty stubs) and linked against libs2mv.so.
+#include "cuda_utils.h"
+#include "d_io.h"
+#else
 #include "../include/s2mv_compat.h"
+#endif
 #include "bmp_io.h"
 
 static double now_s()

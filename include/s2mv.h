@@ -91,15 +91,21 @@ int s2mv_device_sm_count(const s2mv_ctx *ctx);
 int s2mv_process_sbs(s2mv_ctx *ctx, const uint8_t *img_sbs, int num_cols_sbs,
                      float *disp_l, float *disp_r, uint8_t *interlaced);
 
-/* Pageable caller buffers (cv::Mat::data in the reference's drivers) are normally staged through the
- * context's pinned buffers: two extra host copies of 35 MB per 1080p frame (136 instead of 214 frames/s).  With
- * host registration on, each distinct caller buffer is page-locked in place the first time it is seen
- * (cudaHostRegister) and DMA'd directly from then on.  CONTRACT: every buffer passed while it is on must stay
- * allocated until the context is destroyed or registration is switched off (which unregisters everything) --
- * memory freed while registered and handed out again by the allocator would be written through a stale
- * mapping.  For callers that reuse their buffers across frames, as the reference's video loop does.  Off by
- * default; the adcensus_stm shims switch it on when S2MV_HOST_REGISTER=1 is in the environment. */
-int s2mv_set_host_registration(s2mv_ctx *ctx, int on);
+/* Pageable caller buffers (cv::Mat::data in the reference's drivers) are staged through the context's pinned
+ * buffers by default: two extra host copies of 35 MB per 1080p frame.  With host registration a caller buffer
+ * is page-locked in place (cudaHostRegister) and DMA'd directly from then on.  mode:
+ *   0  staged (default of s2mv_create);
+ *   1  always: each distinct buffer is registered the first time it is seen and stays registered until the
+ *      context is destroyed or the mode changes;
+ *   2  auto (what the adcensus_stm / adcensus_stm_2 shims run, unless S2MV_HOST_REGISTER=0): a buffer is
+ *      registered when the SAME pointer arrives in two consecutive calls -- the reference's video loop reuses
+ *      its four buffers for the whole run (video_io.cpp:125-158) -- and unregistered as soon as a call arrives
+ *      without it.
+ * CONTRACT (modes 1 and 2): a buffer must stay allocated while it is registered, i.e. in mode 2 until the
+ * first call that no longer passes it (or the mode changes / the context is destroyed); memory freed while
+ * registered and handed out again by the allocator would be written through a stale mapping.  Changing the
+ * mode unregisters everything. */
+int s2mv_set_host_registration(s2mv_ctx *ctx, int mode);
 
 /* Same work on DEVICE pointers, enqueued on `stream` (a cudaStream_t; NULL =
  * the context's own stream) without synchronising. */

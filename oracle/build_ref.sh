@@ -65,4 +65,98 @@ for p in "${pids[@]}"; do wait "$p"; done
 mv "$TMP/q15/d_dr_irv.o" "$TMP/obj/d_dr_irv.o"
 "$NVCC" -gencode arch=compute_100,code=sm_100 -shared -Xcompiler -fPIC "$TMP"/obj/*.o \
     -o "$OUT/libs2mv_ref_q15.so" -lcudart
-echo "build_ref: wrote $OUT/libs2mv_ref.so and $OUT/libs2mv_ref_q15.so"
+
+# ---------------------------------------------------------------------------------------------
+# Third library: libs2mv_ref_patched.so -- the reference OUTSIDE its validity domain (SURVEY §2.4:
+# W > 1024, H % 32 != 0, num_disp > 65 -- i.e. BASELINE configs 2-4).  Kernel bodies are the
+# reference's; only LAUNCH GEOMETRY changes, on scratch copies under $TMP, each edit checked to have
+# matched.  In-domain (640x384, D=64) this build is bit-identical to libs2mv_ref_q15.so
+# (tests/test_ref_parity.py::test_patched_equals_q15_in_domain).  Deviations, all of them:
+#   P1 d_ca_cross.cu:190     ca_cross_construction_kernel block (num_cols,1) -> (160,1), ceil grid
+#                            (per-pixel, bounds-checked kernel; block = W fails to launch for W > 1024)
+#   P2 d_ca_cross.cu:258,267 cost_transpose_kernel_4 (no bounds checks, grid ceil(H/8)/4 truncates: rows
+#                            never transposed when H % 32 != 0) -> the reference's own bounds-checked
+#                            cost_transpose_kernel (d_ca_cross_sum.cu:135-146), ceil grid
+#   P3 d_dc_wta.cu:45        dc_wta_kernel block (num_cols,1) -> (160,1)
+#   P4 d_dr_dcc.cu:94        dr_dcc/ddc/merge kernels block (num_cols,1) -> (160,1)
+#   P5 d_dr_irv.cu:184-206   int dhist[65], 65 bins scanned -> dhist[512], max(num_disp,65) bins
+#                            (out-of-bounds local writes for num_disp > 65: the only defined reading);
+#      d_dr_irv.cu:169       + the Q15 barrier (as in libs2mv_ref_q15.so);
+#      d_dr_irv.cu:248       pre-kernel block 32x32 -> 32x24: threads of a partial block return before
+#                            they fill their share of the tile (:143-144), so H % 32 != 0 leaves live
+#                            threads reading unfilled rows; 24 divides 384, 1080 and 2160
+#   P6 d_filter_gaussian.cu:140  block 32x32 -> 32x24, same early-return-before-fill pattern (:18-19)
+#   T  d_io.cu               five one-line taps (ref_tap(...), D2H copies into buffers the test registers;
+#                            no-ops otherwise) after aggregation / WTA / cross-check / voting / view
+#                            synthesis, so that the stages can be compared at sizes where only
+#                            adcensus_stm is usable
+#   A  -DcudaMalloc=ref_pool_malloc -DcudaFree=ref_pool_free: the reference's >30 cudaMalloc/cudaFree
+#      pairs per frame go through ref_harness.cu, which forwards them to CUDA unchanged, or -- for the
+#      "allocation hoisted" timing only -- serves them from a size-keyed cache.
+P="$TMP/patched"
+mkdir -p "$P" "$TMP/pobj"
+must() { grep -q "$2" "$1" || { echo "build_ref: patch site missing in $1: $2" >&2; exit 1; }; }
+cp "$REF/d_ca_cross.cu" "$REF/d_dc_wta.cu" "$REF/d_dr_dcc.cu" "$REF/d_filter_gaussian.cu" "$REF/d_io.cu" "$P/"
+cp "$TMP/d_dr_irv_q15.cu" "$P/d_dr_irv.cu"
+sed -i '190s/size_t bw = num_cols;/size_t bw = 160;/' "$P/d_ca_cross.cu"
+sed -i '258s/.*/    cost_transpose_kernel<<<dim3((num_cols + 31) \/ 32, (num_rows + 7) \/ 8, 1), block_sz_t>>>(d_acost, d_cost, num_disp, num_rows, num_cols);/' "$P/d_ca_cross.cu"
+sed -i '267s/.*/    cost_transpose_kernel<<<dim3((num_rows + 31) \/ 32, (num_cols + 7) \/ 8, 1), block_sz_t_v>>>(d_cost, d_acost, num_disp, num_cols, num_rows);/' "$P/d_ca_cross.cu"
+sed -n '258p' "$REF/d_ca_cross.cu" | grep -q 'cost_transpose_kernel_4<<<grid_sz_t, block_sz_t>>>(d_acost, d_cost' || { echo "build_ref: d_ca_cross.cu:258 changed" >&2; exit 1; }
+sed -n '267p' "$REF/d_ca_cross.cu" | grep -q 'cost_transpose_kernel_4<<<grid_sz_t_v, block_sz_t_v>>>(d_cost, d_acost' || { echo "build_ref: d_ca_cross.cu:267 changed" >&2; exit 1; }
+sed -n '190p' "$P/d_ca_cross.cu" | grep -q 'bw = 160' || { echo "build_ref: d_ca_cross.cu:190 changed" >&2; exit 1; }
+sed -i '45s/size_t bw = num_cols;/size_t bw = 160;/' "$P/d_dc_wta.cu";  sed -n '45p' "$P/d_dc_wta.cu" | grep -q 'bw = 160' || { echo "build_ref: d_dc_wta.cu:45 changed" >&2; exit 1; }
+sed -i '94s/size_t bw = num_cols;/size_t bw = 160;/' "$P/d_dr_dcc.cu";  sed -n '94p' "$P/d_dr_dcc.cu" | grep -q 'bw = 160' || { echo "build_ref: d_dr_dcc.cu:94 changed" >&2; exit 1; }
+# d_dr_irv.cu: the q15 copy has one extra line at 169, so the reference's 184-208 are 185-209 and 248 is 249 here
+sed -i '185s/int dhist\[65\];/int dhist[512];/; 186s/i < 65/i < (num_disp > 65 ? num_disp : 65)/; 207s/i < 65/i < (num_disp > 65 ? num_disp : 65)/; 249s/size_t pbh = 32;/size_t pbh = 24;/' "$P/d_dr_irv.cu"
+[ "$(grep -c 'num_disp > 65 ? num_disp : 65' "$P/d_dr_irv.cu")" = 2 ] || { echo "build_ref: d_dr_irv.cu bin loops not patched" >&2; exit 1; }
+must "$P/d_dr_irv.cu" 'int dhist\[512\];'
+must "$P/d_dr_irv.cu" 'size_t pbh = 24;'
+sed -i '140s/size_t bh = 32;/size_t bh = 24;/' "$P/d_filter_gaussian.cu"; sed -n '140p' "$P/d_filter_gaussian.cu" | grep -q 'bh = 24' || { echo "build_ref: d_filter_gaussian.cu:140 changed" >&2; exit 1; }
+# taps (inserted bottom-up so that the line numbers above each insertion stay the reference's)
+chk() { sed -n "$1p" "$REF/d_io.cu" | grep -q "$2" || { echo "build_ref: d_io.cu:$1 changed (expected $2)" >&2; exit 1; }; }
+chk 203 'd_mux_multiview(d_views, d_interlaced'
+chk 150 'd_filter_bilateral_1(d_disp_l, 7, 5, 10'
+chk 147 'd_dr_irv(d_disp_l, d_outliers_l'
+chk 140 'unsigned char \*d_outliers_l, \*d_outliers_r;'
+chk 131 'd_dc_wta(d_adcensus_cost_l, d_disp_l'
+sed -i '203i\    ref_tap_views(h_views, num_views, imgelem_sz); ref_tap(4, d_mask_l, d_mask_r, sizeof(float) * img_sz);' "$P/d_io.cu"
+sed -i '150i\    ref_tap(3, d_disp_l, d_disp_r, sizeof(float) * img_sz); ref_tap(5, d_outliers_l, d_outliers_r, img_sz);' "$P/d_io.cu"
+sed -i '147i\    ref_tap(2, d_outliers_l, d_outliers_r, img_sz);' "$P/d_io.cu"
+sed -i '140i\    ref_tap(1, d_disp_l, d_disp_r, sizeof(float) * img_sz);' "$P/d_io.cu"
+sed -i '131i\    ref_tap(0, d_adcensus_cost_memory, d_adcensus_cost_memory + cost_sz, sizeof(float) * cost_sz); ref_tap(6, d_cross_memory_l, d_cross_memory_r, 4 * img_sz);' "$P/d_io.cu"
+sed -i '3a extern "C" void ref_tap(int id, const void *da, const void *db, size_t bytes);\nextern "C" void ref_tap_views(unsigned char **views, int num_views, size_t bytes);' "$P/d_io.cu"
+[ "$(grep -c 'ref_tap' "$P/d_io.cu")" = 7 ] || { echo "build_ref: d_io.cu taps: expected 7 lines, got $(grep -c 'ref_tap' "$P/d_io.cu")" >&2; exit 1; }
+PFLAGS=("${FLAGS[@]}" -DcudaMalloc=ref_pool_malloc -DcudaFree=ref_pool_free)
+pids=()
+for u in "${UNITS[@]}"; do
+    src="$REF/$u.cu"; [ -f "$P/$u.cu" ] && src="$P/$u.cu"
+    extra=()
+    [ "$u" = d_dr_irv ] && extra=(-maxrregcount=64)
+    "$NVCC" "${PFLAGS[@]}" "${extra[@]}" "$src" -o "$TMP/pobj/$u.o" &
+    pids+=($!)
+done
+"$NVCC" "${PFLAGS[@]}" "$TMP/d_filter_bilateral.cu" -o "$TMP/pobj/d_filter_bilateral.o" &
+pids+=($!)
+"$NVCC" "${FLAGS[@]}" -DREF_PATCHED "$HERE/ref_harness.cu" -o "$TMP/pobj/ref_harness.o" &
+pids+=($!)
+for p in "${pids[@]}"; do wait "$p"; done
+"$NVCC" -gencode arch=compute_100,code=sm_100 -shared -Xcompiler -fPIC "$TMP"/pobj/*.o \
+    -o "$OUT/libs2mv_ref_patched.so" -lcudart
+echo "build_ref: wrote $OUT/libs2mv_ref.so, $OUT/libs2mv_ref_q15.so and $OUT/libs2mv_ref_patched.so"
+# ---------------------------------------------------------------------------------------------
+# Boundary proof: the headless drivers (drivers/s2mv_image.cpp, s2mv_video.cpp -- the call sequences of
+# image_io.cpp:171-292 and video_io.cpp:158) compiled against the REFERENCE's own headers
+# (-DS2MV_REFERENCE_HEADERS: the include lists of image_io.cpp:10-26 / video_io.cpp:11-14 from $REF, OpenCV
+# satisfied by the same empty stubs) and linked against the PRODUCT library.  A prototype that differed from
+# the reference's would fail to link here.  tests/test_drivers.py runs them on the GPU box.
+S2MV_DIR="$HERE/../stereo-to-multiview-cuda_b200"
+if [ -f "$S2MV_DIR/libs2mv.so" ]; then
+    for d in s2mv_image s2mv_video; do
+        "$NVCC" -O2 -std=c++17 -w -x c++ -DS2MV_REFERENCE_HEADERS -I "$TMP/stubs" -I "$REF" "$HERE/../drivers/$d.cpp" \
+            -o "$OUT/${d}_refhdr" -L"$S2MV_DIR" -ls2mv -Xlinker -rpath -Xlinker '$ORIGIN/../../stereo-to-multiview-cuda_b200'
+    done
+    echo "build_ref: wrote $OUT/s2mv_image_refhdr and $OUT/s2mv_video_refhdr (reference headers + libs2mv.so)"
+else
+    echo "build_ref: libs2mv.so not built yet -- skipping the reference-header drivers" >&2
+fi
+

@@ -198,9 +198,15 @@ class Pipeline:
     def last_launch_count(self):
         return self._L.s2mv_last_launch_count(self._ctx)
 
-    def set_host_registration(self, on=True):
-        """Page-lock pageable caller buffers in place (once per buffer) instead of staging them every call."""
-        _check(self._L.s2mv_set_host_registration(self._ctx, int(on)))
+    def set_host_registration(self, mode=True):
+        """Pageable caller buffers: 0 / False = staged through pinned memory every call, 1 / True = page-locked in
+        place the first time they are seen, 2 = auto (page-locked once the same pointer arrives twice in a row,
+        released when it stops arriving) -- s2mv.h has the lifetime contract."""
+        _check(self._L.s2mv_set_host_registration(self._ctx, int(mode)))
+
+    def set_host_registration_auto(self):
+        """What the adcensus_stm shim runs for an unchanged video_io.cpp."""
+        self.set_host_registration(2)
 
     def enable_timing(self, on=True):
         _check(self._L.s2mv_enable_timing(self._ctx, int(on)))

@@ -506,15 +506,16 @@ __global__ void k_band_signal(unsigned int *peer_flag, unsigned int epoch)
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flag), "r"(epoch) : "memory");
 }
-__global__ void k_band_wait(const unsigned int *flag, unsigned int epoch, unsigned int *status)
+__global__ void k_band_wait(const unsigned int *flag, unsigned int epoch, unsigned int *status, long long max_spins)
 {
     unsigned int v = 0;
-    for (long long spin = 0; spin < 20000000; ++spin) {  // ~20 s at 1 us per probe: a late neighbour, not a lost one
+    for (long long spin = 0; spin < max_spins; ++spin) {  // default ~20 s at 1 us per probe: a late neighbour, not a lost one
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if ((int)(v - epoch) >= 0) return;
         __nanosleep(1000);
     }
-    *status = 1u;
+    *status = 1u;  // mapped host memory: every later s2mv_band_* call on this band fails
+    __threadfence_system();
 }
 
 }  // namespace s2mv

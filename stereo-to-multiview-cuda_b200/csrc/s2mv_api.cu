@@ -229,8 +229,15 @@ struct s2mv_ctx {
         size_t view_stride4 = 0;     // neighbour's float4 per view
         void *ipc[3] = {};           // mappings to close (cudaIpcOpenMemHandle)
     } band_peer[2];
-    unsigned int *band_flags = nullptr;  // [0] bumped by the upper neighbour, [1] by the lower, [2] status
+    unsigned int *band_flags = nullptr;  // [0] bumped by the upper neighbour, [1] by the lower
     unsigned int band_epoch = 0;
+    // set to 1 by a k_band_wait whose neighbour never arrived: pinned, mapped host memory, so every later
+    // s2mv_band_* call sees it without synchronising (band_status_d = the device's view of the same word)
+    unsigned int *band_status_h = nullptr, *band_status_d = nullptr;
+    // same-process neighbours that hold pointers into THIS band's volumes (s2mv_band_connect): they are
+    // disconnected before the arena they point into is freed
+    std::vector<s2mv_ctx *> band_attached_by;
+    s2mv_ctx *band_peer_ctx[2] = {};  // the same-process contexts this band stores into (null: IPC or none)
     // two-resolution mode (adcensus_stm_2): this context works at full resolution (no cost volumes), `lo` is a
     // whole context at the disparity resolution
     s2mv_ctx *lo = nullptr;
@@ -274,8 +281,13 @@ struct s2mv_ctx {
     size_t h_sbs_bytes = 0;
     // timing
     // caller buffers page-locked in place (s2mv_set_host_registration): address -> bytes
-    bool host_reg = false;
+    int host_reg = 0;  // 0 staged, 1 page-lock every pageable caller buffer, 2 auto: page-lock the buffers that recur
     std::vector<std::pair<const void *, size_t>> host_regs;
+    const void *host_last[4] = {};  // the previous synchronous call's four caller buffers (auto mode)
+    // test / A-B hooks read from the environment once, at create time
+    int env_irv_dense_min = -1;     // S2MV_IRV_DENSE_MIN (-1: not set)
+    bool env_bilateral_scalar = false;  // S2MV_BILATERAL_SCALAR
+    long long env_band_wait_spins = 20000000;  // S2MV_BAND_WAIT_SPINS: probes (1 us apart) before a halo wait gives up
     cudaEvent_t ev_refined = nullptr;   // disparities final (before DIBR): the synchronous call starts their D2H here
     cudaStream_t st_aux = nullptr;      // second copy stream of the synchronous host call
     cudaEvent_t ev[5] = {};
@@ -310,12 +322,33 @@ static int dev_alloc_t(s2mv_ctx *c, T **p, size_t count) { return dev_alloc(c, (
 static void free_arena(s2mv_ctx *c)
 {
     stream_release(c);
+    // neighbours of this process that store into this arena must stop before it goes away ...
+    for (s2mv_ctx *n : c->band_attached_by)
+        for (int side = 0; side < 2; ++side)
+            if (n->band_peer_ctx[side] == c) {
+                cudaSetDevice(n->device);
+                cudaStreamSynchronize(n->stream);
+                n->band_peer[side] = s2mv_ctx::BandPeer();
+                n->band_peer_ctx[side] = nullptr;
+            }
+    c->band_attached_by.clear();
+    cudaSetDevice(c->device);
+    // ... and this band forgets the neighbours it stored into
+    for (int side = 0; side < 2; ++side) {
+        if (s2mv_ctx *n = c->band_peer_ctx[side]) {
+            auto &v = n->band_attached_by;
+            v.erase(std::remove(v.begin(), v.end(), c), v.end());
+        }
+        c->band_peer_ctx[side] = nullptr;
+    }
     for (auto &pr : c->band_peer) {
         for (void *m : pr.ipc)
             if (m) cudaIpcCloseMemHandle(m);
         pr = s2mv_ctx::BandPeer();
     }
     c->band_flags = nullptr;
+    if (c->band_status_h) cudaFreeHost(c->band_status_h);
+    c->band_status_h = c->band_status_d = nullptr;
     for (void *p : c->allocs) cudaFree(p);
     c->allocs.clear();
     c->arena_bytes = 0;
@@ -346,6 +379,9 @@ extern "C" int s2mv_create(s2mv_ctx **out, int device)
     if (prop.major < 10) return fail(S2MV_ERR_NO_DEVICE, "device %d is sm_%d%d; this build targets sm_100a", device, prop.major, prop.minor);
     CU(cudaSetDevice(device));
     s2mv_ctx *c = new s2mv_ctx();
+    if (const char *e = getenv("S2MV_IRV_DENSE_MIN")) c->env_irv_dense_min = atoi(e) < 0 ? 0 : atoi(e);
+    if (const char *e = getenv("S2MV_BILATERAL_SCALAR")) c->env_bilateral_scalar = atoi(e) != 0;
+    if (const char *e = getenv("S2MV_BAND_WAIT_SPINS")) c->env_band_wait_spins = atoll(e) > 0 ? atoll(e) : 1;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -557,6 +593,9 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
         TRY(dev_alloc_t(c, &c->band_flags, 4));
         CU(cudaMemset(c->band_flags, 0, 4 * sizeof(unsigned int)));
         c->band_epoch = 0;
+        CU(cudaHostAlloc((void **)&c->band_status_h, sizeof(unsigned int), cudaHostAllocMapped));
+        *c->band_status_h = 0;
+        CU(cudaHostGetDevicePointer((void **)&c->band_status_d, c->band_status_h, 0));
     }
     TRY(dev_alloc_t(c, &c->tmask, n));
     TRY(dev_alloc_t(c, &c->lutAd, 768));
@@ -876,7 +915,7 @@ static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2],
     // measured crossover of the two paths at 128 bins: a list of about n/28; the dense path's cost grows with
     // the bin count (bytes per pixel histogram), the sparse one's does not
     a.dense_min = (int)(n / 32) * (c->irv_nbp > 128 ? c->irv_nbp / 128 : 1) + 1;
-    if (const char *e = getenv("S2MV_IRV_DENSE_MIN")) a.dense_min = atoi(e);  // test hook: 0 = always dense, huge = never
+    if (c->env_irv_dense_min >= 0) a.dense_min = c->env_irv_dense_min;  // test hook (read at create): 0 = always dense, huge = never
     for (int v = 0; v < nviews; ++v) a.hseg[v] = dense_ok ? c->irv_hseg[v] : nullptr;
     for (int it = 0; it < iterations; ++it) {
         a.it = it;
@@ -938,8 +977,7 @@ static int launch_bilateral(s2mv_ctx *c, const float *const in[2], float *const 
         constexpr int R = 7, KW = 15, KWP = 16, TWP = (kBil4W + 2 * R + 3) & ~3, TH = kBil4H + 2 * R;
         const size_t smem = ((size_t)TWP * TH + KWP * KW + ncolour) * sizeof(float);
         dim3 g((W + kBil4W - 1) / kBil4W, (H + kBil4H - 1) / kBil4H, nviews);
-        const char *sc = getenv("S2MV_BILATERAL_SCALAR");  // test / A-B hook: 1 = the one-output-at-a-time kernel
-        const bool packed = !(sc && atoi(sc));
+        const bool packed = !c->env_bilateral_scalar;  // test / A-B hook (read at create): the one-output-at-a-time kernel
         if (bounded && packed && h_spatial) {
             const size_t smem2 = ((size_t)2 * TWP * TH + ncolour) * sizeof(float);
             BilPairs<R> w2;
@@ -1216,15 +1254,17 @@ static bool host_register(s2mv_ctx *c, const void *ptr, size_t bytes)
     return false;
 }
 
-extern "C" int s2mv_set_host_registration(s2mv_ctx *c, int on)
+extern "C" int s2mv_set_host_registration(s2mv_ctx *c, int mode)
 {
     if (!c) return fail(S2MV_ERR_BAD_PARAM, "null ctx");
+    if (mode < 0 || mode > 2) return fail(S2MV_ERR_BAD_PARAM, "mode must be 0 (staged), 1 (always) or 2 (auto)");
     CU(cudaSetDevice(c->device));
-    if (!on) {
+    if (mode != c->host_reg) {
         CU(cudaStreamSynchronize(c->stream));
         host_unregister_all(c);
+        for (auto &q : c->host_last) q = nullptr;
     }
-    c->host_reg = on != 0;
+    c->host_reg = mode;
     return S2MV_OK;
 }
 
@@ -1241,6 +1281,14 @@ static int process_host(s2mv_ctx *c, const uint8_t *img_sbs, int num_cols_sbs, f
     const size_t sbs_bytes = (size_t)p.num_rows * num_cols_sbs * 3;
     const size_t out_bytes = (size_t)p.num_rows_out * p.num_cols_out * 3;
     if (c->sbs_bytes < sbs_bytes) {
+        if (c->sbs) {  // regrown (a wider num_cols_sbs): release the old buffer now, not at the next configure
+            CU(cudaStreamSynchronize(c->stream));
+            c->allocs.erase(std::remove(c->allocs.begin(), c->allocs.end(), (void *)c->sbs), c->allocs.end());
+            cudaFree(c->sbs);
+            c->arena_bytes -= c->sbs_bytes;
+            c->sbs = nullptr;
+            c->sbs_bytes = 0;
+        }
         void *d = nullptr;
         CU(cudaMalloc(&d, sbs_bytes));
         c->allocs.push_back(d);
@@ -1270,10 +1318,27 @@ static int process_host(s2mv_ctx *c, const uint8_t *img_sbs, int num_cols_sbs, f
     };
     bool pin_in = is_pinned(img_sbs), pin_dl = is_pinned(disp_l), pin_dr = is_pinned(disp_r), pin_out = is_pinned(interlaced);
     if (c->host_reg) {  // pageable buffers are page-locked in place once and DMA'd directly from then on
-        if (!pin_in) pin_in = host_register(c, img_sbs, sbs_bytes);
-        if (disp_l && !pin_dl) pin_dl = host_register(c, disp_l, n * sizeof(float));
-        if (disp_r && !pin_dr) pin_dr = host_register(c, disp_r, n * sizeof(float));
-        if (interlaced && !pin_out) pin_out = host_register(c, interlaced, out_bytes);
+        // mode 1: every buffer, the first time it is seen.  mode 2 (auto, what the adcensus_stm shim runs): a
+        // buffer is page-locked when the SAME pointer arrives in two consecutive calls -- the pattern of the
+        // reference's video loop, which reuses its four cv::Mat buffers for the whole run (video_io.cpp:125-158)
+        // -- and a registered buffer that stops arriving is unregistered at once (its owner may free it).
+        const void *now[4] = {img_sbs, disp_l, disp_r, interlaced};
+        const size_t nb[4] = {sbs_bytes, n * sizeof(float), n * sizeof(float), out_bytes};
+        bool *pin[4] = {&pin_in, &pin_dl, &pin_dr, &pin_out};
+        if (c->host_reg == 2)
+            for (size_t i = 0; i < c->host_regs.size();) {
+                const void *r = c->host_regs[i].first;
+                if (r != now[0] && r != now[1] && r != now[2] && r != now[3]) {
+                    cudaHostUnregister(const_cast<void *>(r));
+                    cudaGetLastError();
+                    c->host_regs.erase(c->host_regs.begin() + i);
+                } else ++i;
+            }
+        for (int i = 0; i < 4; ++i) {
+            if (!now[i] || *pin[i]) continue;
+            if (c->host_reg == 1 || now[i] == c->host_last[i]) *pin[i] = host_register(c, now[i], nb[i]);
+        }
+        for (int i = 0; i < 4; ++i) c->host_last[i] = now[i];
     }
     if (pin_in) {
         CU(cudaMemcpyAsync(c->sbs, img_sbs, sbs_bytes, cudaMemcpyHostToDevice, st));

@@ -21,6 +21,15 @@ static int band_check(const s2mv_ctx *c)
     return S2MV_OK;
 }
 
+// A wait that ran out leaves the halo rows of that frame stale: every later call on the band fails until it
+// is reconfigured (the word is in mapped host memory: no synchronisation needed to look at it).
+static int band_poisoned(const s2mv_ctx *c)
+{
+    if (c->band_status_h && *(volatile unsigned int *)c->band_status_h)
+        return fail(S2MV_ERR_CUDA, "a neighbouring band never reached the pass this band waited for: the frame is invalid");
+    return S2MV_OK;
+}
+
 extern "C" int s2mv_configure_band(s2mv_ctx *c, const s2mv_params *frame, int band_y0, int band_y1, int apron)
 {
     if (!c || !frame) return fail(S2MV_ERR_BAD_PARAM, "null argument");
@@ -69,6 +78,7 @@ static void band_geometry(const s2mv_ctx *c, RowRange &rr, size_t &row4, size_t 
 extern "C" int s2mv_band_prepare(s2mv_ctx *c, const uint8_t *d_img_sbs_frame, int num_cols_sbs, void *stream)
 {
     TRY(band_check(c));
+    TRY(band_poisoned(c));
     if (!d_img_sbs_frame) return fail(S2MV_ERR_BAD_PARAM, "null frame");
     const s2mv_params &p = c->prm;
     const int H = p.num_rows, W = p.num_cols, V = p.num_views;
@@ -91,6 +101,7 @@ extern "C" int s2mv_band_prepare(s2mv_ctx *c, const uint8_t *d_img_sbs_frame, in
 extern "C" int s2mv_band_pass(s2mv_ctx *c, int pass, void *stream)
 {
     TRY(band_check(c));
+    TRY(band_poisoned(c));
     if (pass < 1 || pass > 4) return fail(S2MV_ERR_BAD_PARAM, "pass must be 1..4");
     CU(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
@@ -109,7 +120,7 @@ extern "C" int s2mv_band_pass(s2mv_ctx *c, int pass, void *stream)
         // the halo rows this pass reads are written by the neighbours' previous pass: wait for their epoch
         for (int side = 0; side < 2; ++side)
             if (c->band_peer[side].connected) {
-                k_band_wait<<<1, 1, 0, st>>>(c->band_flags + side, c->band_epoch, c->band_flags + 2);
+                k_band_wait<<<1, 1, 0, st>>>(c->band_flags + side, c->band_epoch, c->band_status_d, c->env_band_wait_spins);
                 KCHECK();
             }
     }
@@ -185,6 +196,7 @@ extern "C" int s2mv_band_finish(s2mv_ctx *c, float *d_disp_l_band, float *d_disp
                                 void *stream)
 {
     TRY(band_check(c));
+    TRY(band_poisoned(c));
     CU(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     const s2mv_params &p = c->prm;
@@ -232,6 +244,14 @@ extern "C" int s2mv_band_connect(s2mv_ctx *c, int side, s2mv_ctx *peer)
         cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(S2MV_ERR_CUDA, "no peer access %d -> %d: %s", c->device, peer->device, cudaGetErrorString(e));
         cudaGetLastError();
+    }
+    if (c->band_peer_ctx[side] != peer) {
+        if (s2mv_ctx *old = c->band_peer_ctx[side]) {
+            auto &v = old->band_attached_by;
+            v.erase(std::remove(v.begin(), v.end(), c), v.end());
+        }
+        c->band_peer_ctx[side] = peer;
+        peer->band_attached_by.push_back(c);   // peer's free_arena disconnects this band first
     }
     return band_attach(c, side, peer->vol[0], peer->vol[1], peer->band_flags, peer->band_ly0, peer->band_vlo,
                        peer->band_vhi - peer->band_vlo);
@@ -284,15 +304,14 @@ extern "C" int s2mv_band_ipc_connect(s2mv_ctx *c, int side, const s2mv_band_ipc 
     return band_attach(c, side, (float *)m[0], (float *)m[1], (unsigned int *)m[2], peer->local_y0, peer->vlo, peer->vrows);
 }
 
-// 0 when every wait of this band met its neighbour; synchronises the context's stream
+// 0 when every wait of this band met its neighbour; synchronises the stream first, so the answer covers
+// everything enqueued so far.  (s2mv_band_prepare / _pass / _finish look at the same word without
+// synchronising and fail once a wait has run out.)
 extern "C" int s2mv_band_status(s2mv_ctx *c, void *stream)
 {
     TRY(band_check(c));
     CU(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    unsigned int status = 0;
-    CU(cudaMemcpyAsync(&status, c->band_flags + 2, sizeof(status), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (status) return fail(S2MV_ERR_CUDA, "a neighbouring band never reached the pass this band waited for");
-    return S2MV_OK;
+    return band_poisoned(c);
 }

@@ -35,12 +35,12 @@ void adcensus_stm(unsigned char *img_sbs, float *disp_l, float *disp_r, unsigned
     if (!g_ctx) {
         check(s2mv_create(&g_ctx, 0), "adcensus_stm");
         memset(&g_prm, 0, sizeof(g_prm));
-        // The reference's video loop reuses its frame / disparity / output buffers (video_io.cpp:125-137), so
-        // they can be page-locked in place once instead of staging 35 MB through pinned memory every frame
-        // (136 -> 214 frames/s at 1080p).  Opt-in, because it is only safe for buffers that outlive the calls:
-        // S2MV_HOST_REGISTER=1 in the environment of the unchanged driver.
-        if (getenv("S2MV_HOST_REGISTER") && atoi(getenv("S2MV_HOST_REGISTER")) != 0)
-            check(s2mv_set_host_registration(g_ctx, 1), "adcensus_stm");
+        // The reference's video loop reuses its frame / disparity / output buffers (video_io.cpp:125-158): the
+        // shim page-locks a caller buffer in place once the same pointer has arrived twice in a row, instead of
+        // staging 35 MB through pinned memory every frame, and lets go of it when it stops arriving
+        // (s2mv_set_host_registration mode 2, contract in s2mv.h).  S2MV_HOST_REGISTER=0 keeps the staging path.
+        if (!(getenv("S2MV_HOST_REGISTER") && atoi(getenv("S2MV_HOST_REGISTER")) == 0))
+            check(s2mv_set_host_registration(g_ctx, 2), "adcensus_stm");
     }
     if (memcmp(&p, &g_prm, sizeof(p)) != 0) {
         check(s2mv_configure(g_ctx, &p), "adcensus_stm");
@@ -69,8 +69,8 @@ void adcensus_stm_2(unsigned char *img_sbs, float *disp_l, float *disp_r, unsign
     if (!g_ctx2) {
         check(s2mv_create(&g_ctx2, 0), "adcensus_stm_2");
         memset(&g_prm2, 0, sizeof(g_prm2));
-        if (getenv("S2MV_HOST_REGISTER") && atoi(getenv("S2MV_HOST_REGISTER")) != 0)
-            check(s2mv_set_host_registration(g_ctx2, 1), "adcensus_stm_2");
+        if (!(getenv("S2MV_HOST_REGISTER") && atoi(getenv("S2MV_HOST_REGISTER")) == 0))
+            check(s2mv_set_host_registration(g_ctx2, 2), "adcensus_stm_2");
     }
     if (memcmp(&p, &g_prm2, sizeof(p)) != 0 || num_rows_disp != g_rows_disp || num_cols_disp != g_cols_disp ||
         disp_scale != g_disp_scale) {

@@ -256,6 +256,9 @@ class LocalBands:
                 dr[c.y0:c.y1].copy_(br)
                 out[c.y0:c.y1].copy_(bo)
         self._sync()
+        if self.p2p:
+            for c in self.ctx:   # a wait that ran out means stale halo rows: an error, not a frame
+                c.status(self.torch.cuda.current_stream(c.device).cuda_stream)
         return dl, dr, out
 
 
@@ -325,10 +328,13 @@ class DistBand:
         """Raise if any wait of this band ran out before its neighbour arrived (synchronises the stream)."""
         self.ctx.status(self.torch.cuda.current_stream().cuda_stream)
 
-    def process(self, d_sbs, num_cols_sbs, phases=None):
+    def process(self, d_sbs, num_cols_sbs, phases=None, check=True):
         """d_sbs: the whole SBS frame on this rank's GPU.  Returns this band's rows of
-        (disp_l, disp_r, interlaced); everything is enqueued on torch's current stream.  `phases`: a dict that
-        receives the device time (ms) of every phase of this call (adds one synchronisation at the end)."""
+        (disp_l, disp_r, interlaced).  `phases`: a dict that receives the device time (ms) of every phase of
+        this call.  check=True (default): synchronise and raise if a halo wait of this frame ran out before the
+        neighbour arrived (its rows would be stale); check=False leaves everything enqueued on torch's current
+        stream -- the caller then calls check() itself (the next frame's calls fail anyway once a wait has
+        run out)."""
         torch, dist, c = self.torch, self.dist, self.ctx
         st = torch.cuda.current_stream().cuda_stream
         marks = []
@@ -367,4 +373,6 @@ class DistBand:
             marks[-1][1].synchronize()
             for (_, a), (name, b) in zip(marks, marks[1:]):
                 phases[name] = phases.get(name, 0.0) + a.elapsed_time(b)
+        if check and self.transport == "p2p":
+            self.check()
         return self.out_l, self.out_r, self.out_i

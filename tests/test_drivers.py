@@ -12,10 +12,22 @@ from conftest import DEFAULTS, ROOT
 DRV = os.path.join(ROOT, "drivers")
 
 
-@pytest.fixture(scope="module")
-def drivers(s2mv):
-    subprocess.check_call(["make", "-C", DRV, "-s"])
-    return os.path.join(DRV, "s2mv_image"), os.path.join(DRV, "s2mv_video")
+REFHDR = os.path.join(ROOT, "oracle", "_ref")
+
+
+@pytest.fixture(scope="module", params=["compat_header", "reference_headers"])
+def drivers(s2mv, request):
+    """compat_header: drivers/ built against include/s2mv_compat.h.  reference_headers: the SAME sources built
+    against the reference's own headers (image_io.cpp:10-26 / video_io.cpp:11-14 include lists, from
+    /root/reference, by oracle/build_ref.sh in the container) and linked against libs2mv.so -- the proof that
+    the exported prototypes are the reference's, not a hand copy of them."""
+    if request.param == "compat_header":
+        subprocess.check_call(["make", "-C", DRV, "-s"])
+        return os.path.join(DRV, "s2mv_image"), os.path.join(DRV, "s2mv_video")
+    exes = os.path.join(REFHDR, "s2mv_image_refhdr"), os.path.join(REFHDR, "s2mv_video_refhdr")
+    if not all(os.path.exists(e) for e in exes):
+        pytest.skip("oracle/_ref/s2mv_*_refhdr not built (oracle/build_ref.sh needs /root/reference)")
+    return exes
 
 
 def _write_bmp(path, bgr):

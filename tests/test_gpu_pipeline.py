@@ -133,55 +133,53 @@ def digest(*arrays):
     return h.hexdigest()
 
 
-def test_config2_1080p_d128_costvol_vs_oracle(pipe, oracle, fish_sbs, bud_sbs):
-    # BASELINE config 2 geometry: 1920x1080, D=128, zd=64 (bundled 640x384 pair upscaled with the reference's
-    # bilinear formula).  fish is a degenerate pair (identical images), so bud is checked too.
+def _upscaled_1080p(src):
+    from s2mv_b200_pkg import synth
+    L = synth.upscale_bilinear(src[:, :640], 1080, 1920)
+    R = synth.upscale_bilinear(src[:, 640:], 1080, 1920)
+    return np.ascontiguousarray(np.concatenate([L, R], axis=1))
+
+
+def test_config2_1080p_d128_costvol_vs_oracle(pipe, oracle, fish_sbs):
+    # BASELINE config 2 (the bench frame): fish pair upscaled to 1920x1080 with the reference's bilinear
+    # formula, D=128, zd=64 -- the cost-volume entry point alone, WTA disparities bit-exact at full size.
+    # (fish_1 / fish_2 are byte-identical images; the full-frame test below runs the non-degenerate pairs.)
     import torch
-    from s2mv_b200_pkg import synth
-    for src in (fish_sbs, bud_sbs):
-        L = synth.upscale_bilinear(src[:, :640], 1080, 1920)
-        R = synth.upscale_bilinear(src[:, 640:], 1080, 1920)
-        sbs = np.ascontiguousarray(np.concatenate([L, R], axis=1))
-        pipe.configure(num_rows=1080, num_cols=1920, num_disp=128, zero_disp=64, **ALGO)
-        d_sbs = torch.from_numpy(sbs).cuda()
-        d_dl = torch.empty((1080, 1920), dtype=torch.float32, device="cuda")
-        d_dr = torch.empty_like(d_dl)
-        pipe.costvol_device(d_sbs.data_ptr(), 3840, d_dl.data_ptr(), d_dr.data_ptr(), None)
-        pipe.synchronize()
-        odl, odr = oracle.costvol(L, R, 128, 64, luts=pipe.exp_tables(), **{k: ALGO[k] for k in
-                                  ("ad_coeff", "census_coeff", "ucd", "lcd", "usd", "lsd")})
-        assert np.array_equal(d_dl.cpu().numpy(), odl)       # WTA disparities bit-exact at full size
-        assert np.array_equal(d_dr.cpu().numpy(), odr)
-
-
-def test_config3_1080p_full_frame_properties(pipe, oracle):
-    # synthetic 1080p frame (config 3 generator): determinism, value ranges, pass-through of the outer views,
-    # and exact agreement with the oracle on the disparities the DIBR stages consume
-    from s2mv_b200_pkg import synth
-    sbs = synth.make_sbs(1080, 1920, 1000)
+    sbs = _upscaled_1080p(fish_sbs)
     pipe.configure(num_rows=1080, num_cols=1920, num_disp=128, zero_disp=64, **ALGO)
-    pipe.enable_taps(True)
-    a = pipe.adcensus_stm(sbs)
-    taps = pipe.read_taps()
-    b = pipe.adcensus_stm(sbs)
-    pipe.enable_taps(False)
-    assert digest(*a) == digest(*b)
+    d_sbs = torch.from_numpy(sbs).cuda()
+    d_dl = torch.empty((1080, 1920), dtype=torch.float32, device="cuda")
+    d_dr = torch.empty_like(d_dl)
+    pipe.costvol_device(d_sbs.data_ptr(), 3840, d_dl.data_ptr(), d_dr.data_ptr(), None)
+    pipe.synchronize()
+    odl, odr = oracle.costvol(sbs[:, :1920], sbs[:, 1920:], 128, 64, luts=pipe.exp_tables(),
+                              **{k: ALGO[k] for k in ("ad_coeff", "census_coeff", "ucd", "lcd", "usd", "lsd")})
+    assert np.array_equal(d_dl.cpu().numpy(), odl)
+    assert np.array_equal(d_dr.cpu().numpy(), odr)
+
+
+@pytest.mark.parametrize("kind", ["fish_upscaled", "bud_upscaled", "synth_seed1000"])
+def test_1080p_d128_full_frame_every_tap_vs_oracle(pipe, oracle, fish_sbs, bud_sbs, kind):
+    # The headline geometry (1920x1080, D=128, zd=64, 8 views) through the host-buffer call, EVERY output and
+    # tap against the oracle bit for bit: arms, WTA, cross-check labels, voted disparities (both views), masks,
+    # all eight views, both filtered disparity maps and the interlaced frame -- on the bench frame (fish), on a
+    # non-degenerate bundled pair (bud) and on a config-3 stream frame (half of the pixels fail the cross-check).
+    from s2mv_b200_pkg import synth
+    sbs = {"fish_upscaled": lambda: _upscaled_1080p(fish_sbs), "bud_upscaled": lambda: _upscaled_1080p(bud_sbs),
+           "synth_seed1000": lambda: synth.make_sbs(1080, 1920, 1000)}[kind]()
+    got, want = run_both(pipe, oracle, sbs, 1920, 128, 64)
+    assert_frame_equal(got, want)
+    dl, dr, out, taps = got
+    # size-independent properties on top of the equality
     assert np.array_equal(taps["views"][0], sbs[:, 1920:]) and np.array_equal(taps["views"][7], sbs[:, :1920])
     for k in ("wta_l", "wta_r", "irv_l", "irv_r"):
         assert taps[k].min() >= -64 and taps[k].max() <= 63 and np.array_equal(taps[k], np.rint(taps[k]))
-    assert set(np.unique(taps["outliers_l"])) <= {0, 1, 2}
-    assert set(np.unique(taps["mask_l"])) <= {0.0, 1.0}
-    assert a[0].min() >= -64 and a[0].max() <= 63.001
-    # refinement + DIBR replayed on the CPU from the GPU's own WTA disparities
-    D, zd = 128, 64
-    for side in ("l", "r"):
-        arms = taps["arms_" + side]
-        assert np.array_equal(arms, oracle.cross_arms(sbs[:, :1920] if side == "l" else sbs[:, 1920:], 20.0, 6.0, 17, 9))
-    ol, orr = oracle.dcc(taps["wta_l"], taps["wta_r"])
-    assert np.array_equal(ol, taps["outliers_l"]) and np.array_equal(orr, taps["outliers_r"])
-    il, _ = oracle.irv(taps["wta_l"], ol, taps["arms_l"], 20, 0.4, D, zd, 17, 5)
-    assert np.array_equal(il, taps["irv_l"])
-    assert np.array_equal(oracle.bilateral(il, 7, 5.0, 10.0, D), a[0])
+    assert set(np.unique(taps["outliers_l"])) <= {0, 1, 2} and set(np.unique(taps["mask_l"])) <= {0.0, 1.0}
+    assert dl.min() >= -64 and dl.max() <= 63.001
+    if kind != "fish_upscaled":
+        assert (taps["outliers_l"] != 0).mean() > 0.05      # the refinement stages really have work to do
+    again = pipe.adcensus_stm(sbs)
+    assert digest(dl, dr, out) == digest(*again)            # deterministic
 
 
 @pytest.mark.gpu
@@ -271,3 +269,20 @@ def test_host_registration_of_pageable_buffers(s2mv):
         p.set_host_registration(False)                         # unregisters everything; staging again
         got = p.adcensus_stm(frames[0])
         assert all(np.array_equal(a, b) for a, b in zip(got, want[0]))
+        # mode 2 (what the adcensus_stm shim runs): a buffer is page-locked once the same pointer has arrived in
+        # two consecutive calls and released when it stops arriving; the bytes never change
+        p.set_host_registration(2)
+        for rep in range(3):
+            for f, w in zip(frames, want):
+                buf[...] = f
+                p.adcensus_stm_into(buf, dl, dr, out)          # same four pointers every call
+                assert np.array_equal(dl, w[0]) and np.array_equal(dr, w[1]) and np.array_equal(out, w[2])
+        other = np.empty_like(out)
+        p.adcensus_stm_into(keep[1], dl, dr, other)            # two pointers change: the old ones are let go
+        assert np.array_equal(other, want[1][2])
+        del buf                                                # ... so their owner may free them
+        p.adcensus_stm_into(keep[2], dl, dr, other)
+        assert np.array_equal(other, want[2][2])
+        with pytest.raises(s2mv.S2mvError):
+            p.set_host_registration(3)
+        p.set_host_registration(0)

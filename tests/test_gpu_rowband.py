@@ -81,3 +81,70 @@ def test_bands_on_two_devices_in_one_process(s2mv, p2p):
                 c.status()
     finally:
         lb.close()
+
+
+def test_lost_neighbour_is_an_error_not_a_frame(s2mv, monkeypatch):
+    """A halo wait that runs out (the neighbouring band never ran its pass) must surface as an error from
+    s2mv_band_status and from every later call on that band, never as a silently wrong frame."""
+    import torch
+    from s2mv_b200_pkg import rowband, synth
+    monkeypatch.setenv("S2MV_BAND_WAIT_SPINS", "2000")           # ~2 ms instead of ~20 s; read at s2mv_create
+    H, W, D, zd = 200, 192, 32, 16
+    params = dict(num_rows=H, num_cols=W, num_disp=D, zero_disp=zd, num_views=8, angle=18, **ALGO)
+    sbs = torch.from_numpy(synth.make_sbs(H, W, 91)).cuda()
+    lb = rowband.LocalBands([0, 0], p2p=True, **params)
+    try:
+        a, b = lb.ctx
+        a.prepare(sbs.data_ptr(), 2 * W)
+        a.run_pass(1)
+        a.run_pass(2)                                            # waits for band b's pass 1, which never runs
+        with pytest.raises(s2mv.S2mvError, match="never reached"):
+            a.status()
+        with pytest.raises(s2mv.S2mvError, match="never reached"):
+            a.run_pass(3)                                        # poisoned until reconfigured
+        with pytest.raises(s2mv.S2mvError):
+            a.finish(None, None, None)
+    finally:
+        lb.close()
+
+
+def test_closing_a_band_disconnects_its_neighbours(s2mv):
+    """Destroying (or reconfiguring) a band must not leave its neighbours storing halo rows into freed memory:
+    the survivors fall back to running without that neighbour."""
+    import torch
+    from s2mv_b200_pkg import rowband, synth
+    H, W, D, zd = 200, 192, 32, 16
+    params = dict(num_rows=H, num_cols=W, num_disp=D, zero_disp=zd, num_views=8, angle=18, **ALGO)
+    sbs = torch.from_numpy(synth.make_sbs(H, W, 92)).cuda()
+    lb = rowband.LocalBands([0, 0], p2p=True, **params)
+    a, b = lb.ctx
+    b.close()                                                    # frees b's volumes; a must let go of them
+    try:
+        a.prepare(sbs.data_ptr(), 2 * W)
+        for k in (1, 2, 3, 4):
+            a.run_pass(k)                                        # no peer stores, no waits: nothing to hang on
+        a.status()
+        torch.cuda.synchronize()
+    finally:
+        a.close()
+
+
+def test_dist_band_two_processes_ipc(s2mv):
+    """DistBand as it runs on the box: one process per GPU under torchrun, neighbours' volumes mapped through
+    CUDA IPC, halo rows as peer stores over NVLink; outputs bit for bit the single-context frame.  Needs two
+    GPUs (skipped on the one-GPU test box)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29617", os.path.join(root, "tools", "rowband_bench.py"), "--height", "432", "--width", "640",
+           "--disp", "96", "--steps", "2", "--warmup", "1", "--check", "--transport", "p2p"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    import json
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert res["n_gpus"] == 2 and all(res["check"].values()), res

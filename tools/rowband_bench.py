@@ -43,6 +43,15 @@ def main():
     ap.add_argument("--single", action="store_true", help="N = 1 only: time the ordinary single-context frame "
                                                           "(chunk-sequential volumes when needed) instead of one band")
     args = ap.parse_args()
+    res = measure(args)
+    if res is not None:
+        print(json.dumps(res), flush=True)
+    return 0
+
+
+def measure(args):
+    """One row-band measurement; every rank calls it, rank 0 gets the result dict (others None).
+    `args` needs: height width disp seed steps warmup check baseline transport sha single."""
     rank, world, local_rank = sharding.dist_env()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -76,8 +85,7 @@ def main():
                    "chunk_sequential": p.chunk_sequential,
                    "sha": {k: hashlib.sha256(t.cpu().numpy().tobytes()).hexdigest() for k, t in
                            (("disp_l", d_dl), ("disp_r", d_dr), ("interlaced", d_out))}}
-        print(json.dumps(res), flush=True)
-        return 0
+        return res
 
     band = rowband.DistBand(local_rank, rank, world, transport=args.transport, **params)
     for _ in range(args.warmup):
@@ -89,7 +97,7 @@ def main():
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        out_l, out_r, out_i = band.process(d_sbs, 2 * W)
+        out_l, out_r, out_i = band.process(d_sbs, 2 * W, check=False)
         b.record()
         b.synchronize()
         ms += sharding.reduce_scalar(a.elapsed_time(b), "max", dev)
@@ -161,9 +169,7 @@ def main():
     else:
         band.close()
     sharding.barrier()
-    if rank == 0:
-        print(json.dumps(res), flush=True)
-    return 0
+    return res if rank == 0 else None
 
 
 if __name__ == "__main__":
