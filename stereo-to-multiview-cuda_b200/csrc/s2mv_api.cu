@@ -4,6 +4,7 @@
 // and synchronises the device ~25 times per frame (d_io.cu:43-237).  Here one
 // context owns one arena sized at configure time; a frame is a fixed sequence
 // of launches on one stream with no host synchronisation inside it.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -20,6 +21,7 @@
 #include "kernels_cost.cuh"
 #include "kernels_dibr.cuh"
 #include "kernels_line.cuh"
+#include "kernels_line2.cuh"
 #include "kernels_prep.cuh"
 #include "kernels_refine.cuh"
 #include "kernels_so.cuh"
@@ -123,7 +125,23 @@ struct CostPlan {
     size_t smem_ci;                     // CI-only stage kernels (k_hpass)
     int S_h, S_h4, S_v;                 // outputs per CTA along a row (pass 1 / pass 4) / a column (k_line)
     size_t smem_line_ci, smem_line_h, smem_line_h4, smem_line_v;
+    // k_line2 (persistent, pipelined; LP = 32 only): tile geometry per pass kind, 0 = not available
+    bool line2;
+    int l2_HP, l2_S_ci, l2_S_h, l2_S_v;
+    size_t l2_smem_ci, l2_smem_h, l2_smem_v;
 };
+
+constexpr int kL2B = 6, kL2NW = 16;        // loaded-tile passes: 16 consumer warps, 6 outputs per block
+constexpr int kL2BCi = 8, kL2NWCi = 12;    // pass 1 (tiles are computed): 12 consumer warps, 8 outputs per block
+
+// outputs per tile along a line of `len` outputs: close to 96, a multiple of the block size, the line cut evenly
+static int line2_segment(int len, int B)
+{
+    const int nseg = (len + 95) / 96;
+    int S = (len + nseg - 1) / nseg;
+    S = ((S + B - 1) / B) * B;
+    return S < B ? B : S;
+}
 
 static size_t hpass_smem(int S, int halo, int Dc, int M, bool ci)
 {
@@ -204,6 +222,19 @@ static int make_plan(CostPlan &pl, int H, int W, int D, int zd, int usd, int sm_
     pl.S_h4 = pick_line_segment(W, usd, pl.LP, false, &pl.smem_line_h4, 0);
     pl.S_v = pick_line_segment(H, usd, pl.LP, false, &pl.smem_line_v);
     if (!pl.S_h || !pl.S_v || !pl.S_h4) return fail(S2MV_ERR_BAD_PARAM, "usd too large for the shared-memory tile");
+    // persistent pipelined line kernel: one warp per pixel (128 disparities per chunk), three tiles per SM
+    pl.line2 = false;
+    if (pl.LP == 32) {
+        pl.l2_HP = (usd + 1) & ~1;
+        pl.l2_S_ci = line2_segment(W, kL2BCi);
+        pl.l2_S_h = line2_segment(W, kL2B);
+        pl.l2_S_v = line2_segment(H, kL2B);
+        pl.l2_smem_ci = line2_smem_bytes(pl.l2_S_ci, pl.l2_HP, kL2BCi, true);
+        pl.l2_smem_h = line2_smem_bytes(pl.l2_S_h, pl.l2_HP, kL2B, false);
+        pl.l2_smem_v = line2_smem_bytes(pl.l2_S_v, pl.l2_HP, kL2B, false);
+        const size_t cap = 227 * 1024;
+        pl.line2 = pl.l2_smem_ci <= cap && pl.l2_smem_h <= cap && pl.l2_smem_v <= cap;
+    }
     return S2MV_OK;
 }
 
@@ -287,6 +318,11 @@ struct s2mv_ctx {
     // test / A-B hooks read from the environment once, at create time
     int env_irv_dense_min = -1;     // S2MV_IRV_DENSE_MIN (-1: not set)
     bool env_bilateral_scalar = false;  // S2MV_BILATERAL_SCALAR
+    bool env_line_v1 = false;           // S2MV_LINE_V1: the first form of the cost-volume kernel (k_line) for every plan
+    bool env_line_bulk = false;         // S2MV_LINE_BULK: k_line2 with per-position bulk copies instead of the tensor map
+    int *line_ctr = nullptr;            // k_line2 work counters, one per pass
+    CUtensorMap tmap_vol[2][2];         // tensor maps of the ping-pong volumes: [buffer A/B][row tile / column tile]
+    bool tmap_ok = false;
     long long env_band_wait_spins = 20000000;  // S2MV_BAND_WAIT_SPINS: probes (1 us apart) before a halo wait gives up
     cudaEvent_t ev_refined = nullptr;   // disparities final (before DIBR): the synchronous call starts their D2H here
     cudaStream_t st_aux = nullptr;      // second copy stream of the synchronous host call
@@ -381,6 +417,8 @@ extern "C" int s2mv_create(s2mv_ctx **out, int device)
     s2mv_ctx *c = new s2mv_ctx();
     if (const char *e = getenv("S2MV_IRV_DENSE_MIN")) c->env_irv_dense_min = atoi(e) < 0 ? 0 : atoi(e);
     if (const char *e = getenv("S2MV_BILATERAL_SCALAR")) c->env_bilateral_scalar = atoi(e) != 0;
+    if (const char *e = getenv("S2MV_LINE_V1")) c->env_line_v1 = atoi(e) != 0;
+    if (const char *e = getenv("S2MV_LINE_BULK")) c->env_line_bulk = atoi(e) != 0;
     if (const char *e = getenv("S2MV_BAND_WAIT_SPINS")) c->env_band_wait_spins = atoll(e) > 0 ? atoll(e) : 1;
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
@@ -448,6 +486,10 @@ static int set_kernel_attrs()
     TRY(set_line_attrs<8>());
     TRY(set_line_attrs<16>());
     TRY(set_line_attrs<32>());
+    TRY(set_smem(k_line2<LM_CI_H, kL2NWCi, kL2BCi>, big));
+    TRY(set_smem(k_line2<LM_H, kL2NW, kL2B>, big));
+    TRY(set_smem(k_line2<LM_H_WTA, kL2NW, kL2B>, big));
+    TRY(set_smem(k_line2<LM_V, kL2NW, kL2B>, big));
     TRY(set_smem(k_bilateral, 160 * 1024));
     TRY(set_smem(k_bilateral4<7, true>, 64 * 1024));
     TRY(set_smem(k_bilateral4<7, false>, 64 * 1024));
@@ -503,6 +545,51 @@ extern "C" int s2mv_configure(s2mv_ctx *c, const s2mv_params *p)
         c->no_volume = false;
     }
     return configure_impl(c, p, nullptr);
+}
+
+// Tensor maps for k_line2's tile loads: the volume as a 4-D tensor [view][row][column][disparity] of fp32, box =
+// one tile (P positions of one line x 128 disparities).  cuTensorMapEncodeTiled is a driver entry point; it is
+// resolved through the runtime, so the library does not link against libcuda.  Without it (or on an encoding
+// error) the kernel falls back to one 512-byte bulk copy per tile position.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+static bool make_volume_tmaps(s2mv_ctx *c, size_t vol_rows)
+{
+    const CostPlan &pl = c->plan;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || !pl.line2 || c->no_volume) return false;
+    const cuuint64_t W = (cuuint64_t)c->prm.num_cols, dfl = (cuuint64_t)pl.LPtot * 4;
+    const cuuint64_t gdim[4] = {dfl, W, (cuuint64_t)vol_rows, 2};
+    const cuuint64_t gstr[3] = {dfl * 4, dfl * 4 * W, dfl * 4 * W * (cuuint64_t)vol_rows};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    for (int buf = 0; buf < 2; ++buf)
+        for (int vert = 0; vert < 2; ++vert) {
+            const cuuint32_t P = (cuuint32_t)((vert ? pl.l2_S_v : pl.l2_S_h) + 2 * pl.l2_HP);
+            if (P > 256) return false;
+            const cuuint32_t box[4] = {128, vert ? 1u : P, vert ? P : 1u, 1};
+            CUresult r = enc(&c->tmap_vol[buf][vert], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->vol[buf], gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return false;
+        }
+    return true;
 }
 
 static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *band)
@@ -589,6 +676,7 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
         }
     }
     TRY(dev_alloc_t(c, &c->irv_count, 8 + 2 * 64));
+    TRY(dev_alloc_t(c, &c->line_ctr, 8));
     if (band) {
         TRY(dev_alloc_t(c, &c->band_flags, 4));
         CU(cudaMemset(c->band_flags, 0, 4 * sizeof(unsigned int)));
@@ -618,6 +706,7 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
     }
     TRY(build_luts(c, p->ad_coeff, p->census_coeff, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    c->tmap_ok = make_volume_tmaps(c, vol_rows);
     c->configured = true;
     return S2MV_OK;
 }
@@ -765,6 +854,42 @@ static int launch_pass(s2mv_ctx *c, LineArgs a, int pass, float4 *A, float4 *B, 
     float4 *out_base = ((pass == 1 || pass == 3) ? A : B) - bias;
     for (int v = 0; v < nviews; ++v) { a.in[v] = in_base + v * view_stride4; a.out[v] = out_base + v * view_stride4; }
     a.v_begin = rr.own0; a.v_end = rr.own1; a.v_lo = rr.vlo; a.v_hi = rr.vhi;
+    if (pl.line2 && !c->env_line_v1) {
+        // persistent pipelined kernel: one CTA per SM, lines handed out through a counter zeroed on the stream
+        const bool vert = pass == 2 || pass == 3, ci = pass == 1 && from_ci;
+        Line2Args L;
+        memset(&L, 0, sizeof(L));
+        a.ln_first = vert ? 0 : rr.own0;
+        L.a = a;
+        L.S = vert ? pl.l2_S_v : (ci ? pl.l2_S_ci : pl.l2_S_h);
+        L.HP = pl.l2_HP;
+        L.P = L.S + 2 * L.HP;
+        const int len = vert ? rows : W;
+        L.tiles_per_line = (len + L.S - 1) / L.S;
+        L.claims_per_line = vert ? 1 : std::max(1, (L.tiles_per_line + 5) / 10);
+        L.tiles_per_claim = (L.tiles_per_line + L.claims_per_line - 1) / L.claims_per_line;
+        L.nlines = vert ? W : rows;
+        L.nz = nviews * a.nchunks;
+        L.nclaims = L.nz * L.nlines * L.claims_per_line;
+        L.counter = c->line_ctr + pass;
+        // the tile source: passes 1 (stage API) and 3 read buffer B, passes 2 and 4 buffer A
+        const float4 *src = (pass == 1 || pass == 3) ? B : A;
+        const int src_buf = src == reinterpret_cast<float4 *>(c->vol[1]) ? 1 : 0;
+        const bool own_vol = src == reinterpret_cast<float4 *>(c->vol[src_buf]) && W == c->prm.num_cols &&
+                             (nviews == 1 || view_stride4 == (size_t)(rr.vhi - rr.vlo) * W * pl.LPtot);
+        L.use_tmap = c->tmap_ok && !ci && own_vol && !c->env_line_bulk;
+        L.row_bias = rr.vlo;
+        const CUtensorMap &tm = c->tmap_vol[src_buf][vert ? 1 : 0];
+        CU(cudaMemsetAsync(L.counter, 0, sizeof(int), st));
+        const int grid = std::min(c->sm_count, L.nclaims);
+        if (ci) k_line2<LM_CI_H, kL2NWCi, kL2BCi><<<grid, (kL2NWCi + 1) * 32, pl.l2_smem_ci, st>>>(L, tm);
+        else if (vert) k_line2<LM_V, kL2NW, kL2B><<<grid, (kL2NW + 1) * 32, pl.l2_smem_v, st>>>(L, tm);
+        else if (pass == 4 && to_wta) k_line2<LM_H_WTA, kL2NW, kL2B><<<grid, (kL2NW + 1) * 32, pl.l2_smem_h, st>>>(L, tm);
+        else k_line2<LM_H, kL2NW, kL2B><<<grid, (kL2NW + 1) * 32, pl.l2_smem_h, st>>>(L, tm);
+        KCHECK();
+        c->launches += 1;
+        return S2MV_OK;
+    }
     if (pass == 1 || pass == 4) {
         const int S = pass == 1 ? pl.S_h : pl.S_h4;
         const dim3 gh((W + S - 1) / S, rows, nviews * a.nchunks);
