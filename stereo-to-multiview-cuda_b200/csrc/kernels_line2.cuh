@@ -34,7 +34,6 @@
 
 namespace s2mv {
 
-constexpr int kL2Stages = 3;
 constexpr int kL2MaxConsumers = 16;
 constexpr int kL2DescRing = 8;
 constexpr int kL2MaxBlocks = 16;       // output blocks per tile (S / B)
@@ -128,7 +127,7 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr)
 // shared-memory carve-up of one CTA (every section 16-byte aligned); the kernel walks the same list
 __host__ __device__ inline size_t line2_align16(size_t b) { return (b + 15) & ~(size_t)15; }
 __host__ __device__ inline int line2_frame(int B, int HP) { return (B + 2 * HP + 1) & ~1; }  // mask positions per block
-__host__ __device__ inline size_t line2_smem_bytes(int S, int HP, int B, bool ci)
+__host__ __device__ inline size_t line2_smem_bytes(int S, int HP, int B, bool ci, int kL2Stages)
 {
     const size_t P = (size_t)S + 2 * HP;
     size_t b = 128;                                                                     // alignment slack of the tile base
@@ -137,7 +136,8 @@ __host__ __device__ inline size_t line2_smem_bytes(int S, int HP, int B, bool ci
     b += line2_align16(kL2DescRing * sizeof(Line2Desc));                                // descriptors
     b += line2_align16((size_t)kL2DescRing * kL2MaxBlocks * line2_frame(B, HP) * 2);    // window masks (u16)
     b += line2_align16((size_t)kL2DescRing * kL2MaxBlocks * 4);                         // walk bounds per block
-    if (ci) b += line2_align16(kL2Stages * (4 * P + 256) * 4) + 80 * 4;                 // operand words, census table
+    b += line2_align16(kL2Stages * (ci ? (4 * P + 256) * 4 : 0)) + 80 * 4;              // operand words, census table
+    b += kL2DescRing * 4;                                                               // claimed runs (producer warps)
     return b;
 }
 
@@ -228,42 +228,46 @@ __device__ __forceinline__ void ci_fill_groups2(float4 *__restrict__ C4, const u
     }
 }
 
-// ---------------------------------------------------------------- window masks (producer warp)
+// ---------------------------------------------------------------- window masks (producer warps)
 // Masks of one tile: block b = outputs b*B .. b*B+B-1, frame position k = tile position b*B + k (every window of
 // the block lies inside [0, B + 2*HP): arms <= usd <= HP).  Bit i+1 of mask[b][k] = frame position k inside the
-// window of output i, [i + HP - A_i, i + HP + B_i).  Lane l works on block l % 16, half l / 16 of the frame; the
-// lower-half lane also writes the block's walk bounds (first position | end position << 16; 0 = nothing to add).
+// window of output i, [i + HP - A_i, i + HP + B_i).  The kL2Producers warps split the blocks between them; inside
+// a warp, 8 lanes share a block and split its frame.  The first lane of a block also writes the block's walk
+// bounds (first position | end position << 16; 0 = nothing to add).
+constexpr int kL2Producers = 4;
 template <int B, bool VERT>
 __device__ __forceinline__ void build_masks(uint16_t *__restrict__ masks, uint32_t *__restrict__ bounds,
                                             const uint32_t *__restrict__ arms, int W, int ln, int t0, int S, int Sact, int HP,
-                                            int lane)
+                                            int pw, int lane)
 {
-    const int FR = line2_frame(B, HP), FH = FR / 2;
-    const int b = lane & (kL2MaxBlocks - 1), h = lane >> 4;
-    if (b * B >= S) return;
-    uint32_t s_rel[B], len[B];
-    int first = 0x7fffffff, end = 0;
+    const int FR = line2_frame(B, HP), PL = (FR + 7) / 8;
+    const int slice = lane & 7;
+    for (int b = pw * 4 + (lane >> 3); b * B < S; b += 4 * kL2Producers) {
+        uint32_t s_rel[B], len[B];
+        int first = 0x7fffffff, end = 0;
 #pragma unroll
-    for (int i = 0; i < B; ++i) {
-        const int o = b * B + i;
-        uint32_t ar = 0u;
-        if (o < Sact) ar = __ldg(arms + (VERT ? (size_t)(t0 + o) * W + ln : (size_t)ln * W + (t0 + o)));
-        const int A = VERT ? arm_up(ar) : arm_left(ar), Bn = VERT ? arm_down(ar) : arm_right(ar);
-        s_rel[i] = (uint32_t)(i + HP - A);
-        len[i] = (uint32_t)(A + Bn);
-        if (A + Bn > 0) {
-            first = min(first, i + HP - A);
-            end = max(end, i + HP + Bn);
+        for (int i = 0; i < B; ++i) {
+            const int o = b * B + i;
+            uint32_t ar = 0u;
+            if (o < Sact) ar = __ldg(arms + (VERT ? (size_t)(t0 + o) * W + ln : (size_t)ln * W + (t0 + o)));
+            const int A = VERT ? arm_up(ar) : arm_left(ar), Bn = VERT ? arm_down(ar) : arm_right(ar);
+            s_rel[i] = (uint32_t)(i + HP - A);
+            len[i] = (uint32_t)(A + Bn);
+            if (A + Bn > 0) {
+                first = min(first, i + HP - A);
+                end = max(end, i + HP + Bn);
+            }
         }
-    }
-    uint16_t *mrow = masks + (size_t)b * FR;
-    for (int k = h * FH; k < (h + 1) * FH; ++k) {
-        uint32_t m = 0;
+        uint16_t *mrow = masks + (size_t)b * FR;
+        const int k1 = min(FR, (slice + 1) * PL);
+        for (int k = slice * PL; k < k1; ++k) {
+            uint32_t m = 0;
 #pragma unroll
-        for (int i = 0; i < B; ++i) m |= (((uint32_t)k - s_rel[i]) < len[i]) ? (2u << i) : 0u;
-        mrow[k] = (uint16_t)m;
+            for (int i = 0; i < B; ++i) m |= (((uint32_t)k - s_rel[i]) < len[i]) ? (2u << i) : 0u;
+            mrow[k] = (uint16_t)m;
+        }
+        if (slice == 0) bounds[b] = end > 0 ? ((uint32_t)first | ((uint32_t)end << 16)) : 0u;
     }
-    if (h == 0) bounds[b] = end > 0 ? ((uint32_t)first | ((uint32_t)end << 16)) : 0u;
 }
 
 // ---------------------------------------------------------------- the window walk of one output block
@@ -327,14 +331,13 @@ __device__ __forceinline__ void wta_block(const float4 acc[B], const LineArgs &a
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int MODE, int NW, int B>
-__global__ void __launch_bounds__((NW + 1) * 32, 1)
+template <int MODE, int NW, int B, int NS>
+__global__ void __launch_bounds__((NW + kL2Producers) * 32, 1)
 k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(16) unsigned char smem_l2[];
     constexpr bool VERT = (MODE == LM_V);
     constexpr bool CI = (MODE == LM_CI_H);
-    constexpr int NS = kL2Stages;
     const LineArgs &a = L.a;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = L.S, HP = L.HP, P = L.P, W = a.W;
@@ -343,7 +346,7 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
     unsigned char *smem_raw = smem_l2 + ((128u - (smem_u32(smem_l2) & 127u)) & 127u);
     const uint32_t tile_bytes = (uint32_t)P * kL2PosBytes;
     unsigned char *sp = smem_raw + (size_t)NS * tile_bytes;
-    const uint32_t bars = smem_u32(sp);  // [0..2] full, [3..5] empty, [6..8] fullO, [9..11] emptyO
+    const uint32_t bars = smem_u32(sp);  // [0..NS) full, then empty, fullO, emptyO (NS <= 4)
     sp += 128;
     Line2Desc *desc = reinterpret_cast<Line2Desc *>(sp);
     sp += line2_align16(kL2DescRing * sizeof(Line2Desc));
@@ -353,19 +356,20 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
     uint32_t *sBounds = reinterpret_cast<uint32_t *>(sp);  // [ring][block]
     sp += line2_align16((size_t)kL2DescRing * kL2MaxBlocks * 4);
     uint32_t *sOps = reinterpret_cast<uint32_t *>(sp);  // CI: per stage ownP[P] ownC[P] othP[P+128] othC[P+128]
-    const int OPS = 4 * P + 256;
+    const int OPS = CI ? 4 * P + 256 : 0;
     float *sLutCen = reinterpret_cast<float *>(sp + line2_align16((size_t)NS * OPS * 4));
 
     auto full = [&](int s) { return bars + 8u * s; };
-    auto empty = [&](int s) { return bars + 8u * (3 + s); };
-    auto fullO = [&](int s) { return bars + 8u * (6 + s); };
-    auto emptyO = [&](int s) { return bars + 8u * (9 + s); };
+    auto empty = [&](int s) { return bars + 8u * (NS + s); };
+    auto fullO = [&](int s) { return bars + 8u * (2 * NS + s); };
+    auto emptyO = [&](int s) { return bars + 8u * (3 * NS + s); };
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
-            mbar_init(full(s), CI ? NW : 33);  // CI: the consumer warps complete a tile; else 32 producer lanes + the copy's bytes
+            // CI: the consumer warps complete a tile; else every producer lane (masks written) + the copy's bytes
+            mbar_init(full(s), CI ? NW : 32 * kL2Producers + 1);
             mbar_init(empty(s), NW);
-            mbar_init(fullO(s), 64);            // per producer lane: its cp.async landed + its masks written
+            mbar_init(fullO(s), 64 * kL2Producers);  // per producer lane: its cp.async landed + its masks written
             mbar_init(emptyO(s), NW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -378,17 +382,30 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
     const int LINE0 = VERT ? a.v_begin : 0;
     const int IN_LO = VERT ? a.v_lo : 0, IN_HI = VERT ? a.v_hi : W;
 
-    // =========================================================== producer warp
-    if (warp == NW) {
-        int seg = 0, seg_end = 0, ln = 0, vslot = 0, chunk = 0, first = 0;
+    // =========================================================== producer warps
+    // All of them walk the same tile sequence (every warp claims through its own shared-memory copy of the run
+    // the leader fetched); the leader (first producer warp) also writes the descriptor and starts the copy.
+    if (warp >= NW) {
+        const int pw = warp - NW;
+        volatile int *sClaim = reinterpret_cast<volatile int *>(sp + line2_align16((size_t)NS * OPS * 4) + 80 * 4);  // [kL2DescRing]
+        int seg = 0, seg_end = 0, ln = 0, vslot = 0, chunk = 0, first = 0, nclaim = 0;
         for (int m = 0;; ++m) {
             const int st = m % NS, ring = m % kL2DescRing;
             if (m >= NS) mbar_wait(CI ? emptyO(st) : empty(st), ((m / NS) - 1) & 1);
             int valid = 1;
             if (seg == seg_end) {  // next run of consecutive segments
+                // the leader draws it from the global counter and hands it to the other producer warps
                 int c = 0;
-                if (lane == 0) c = atomicAdd(L.counter, 1);
-                c = __shfl_sync(0xffffffffu, c, 0);
+                if (pw == 0) {
+                    if (lane == 0) {
+                        c = atomicAdd(L.counter, 1);
+                        sClaim[nclaim % kL2DescRing] = c;
+                    }
+                    __syncwarp();
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kL2Producers) : "memory");
+                c = sClaim[nclaim % kL2DescRing];
+                ++nclaim;
                 if (c >= L.nclaims) {
                     valid = 0;
                 } else {
@@ -405,13 +422,13 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
             }
             const int t0 = LINE0 + seg * S;
             const int Sact = valid ? min(S, LEN - t0) : 0;
-            if (lane == 0) {
+            if (pw == 0 && lane == 0) {
                 Line2Desc d;
                 d.valid = valid; d.ln = ln; d.seg = seg; d.vslot = vslot; d.chunk = chunk; d.t0 = t0; d.Sact = Sact; d.first = first;
                 desc[ring] = d;
             }
             const uint32_t bar = CI ? fullO(st) : full(st);
-            if (!CI && lane == 0) {
+            if (!CI && pw == 0 && lane == 0) {
                 // tile <- volume.  Positions outside the readable part of the line are never inside a window.
                 if (!valid) {
                     mbar_arrive_expect_tx(bar, 0u);
@@ -422,7 +439,7 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
                     else tma_load_4d(dst, &tmap, chunk * 128, t0 - HP, ln - L.row_bias, vslot, bar);
                 }
             }
-            if (!CI && valid && !L.use_tmap) {
+            if (!CI && valid && !L.use_tmap && pw == 0) {
                 const int p_lo = max(0, IN_LO + HP - t0), p_hi = min(P, IN_HI - t0 + HP);
                 const int np = max(p_hi - p_lo, 0);
                 if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)np * kL2PosBytes);
@@ -447,19 +464,20 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
                     const uint32_t o0 = smem_u32(sOps + (size_t)st * OPS);
                     // a continued run only needs the operands of its S new positions; the first tile all of them
                     const int i0 = first ? 0 : 2 * HP;
-                    for (int i = i0 + lane; i < P; i += 32) {
+                    const int pl = pw * 32 + lane;
+                    for (int i = i0 + pl; i < P; i += 32 * kL2Producers) {
                         const int x = clampi(xb + i, 0, W - 1);
                         cp_async4(o0 + 4u * i, gOwnP + x, 4u);
                         cp_async4(o0 + 4u * (P + i), gOwnC + x, 4u);
                     }
-                    for (int i = i0 + lane; i < P + 128; i += 32) {
+                    for (int i = i0 + pl; i < P + 128; i += 32 * kL2Producers) {
                         const int x = clampi(xo + i, 0, W - 1);
                         cp_async4(o0 + 4u * (2 * P + i), gOthP + x, 4u);
                         cp_async4(o0 + 4u * (3 * P + 128 + i), gOthC + x, 4u);
                     }
                 }
                 build_masks<B, VERT>(sMask + (size_t)ring * kL2MaxBlocks * FR, sBounds + ring * kL2MaxBlocks, a.arms[vslot], W, ln, t0,
-                                     S, Sact, HP, lane);
+                                     S, Sact, HP, pw, lane);
             }
             if (CI) cp_async_arrive_noinc(bar);
             mbar_arrive(bar);  // releases this lane's masks (lane 0: and the descriptor)

@@ -127,17 +127,22 @@ struct CostPlan {
     size_t smem_line_ci, smem_line_h, smem_line_h4, smem_line_v;
     // k_line2 (persistent, pipelined; LP = 32 only): tile geometry per pass kind, 0 = not available
     bool line2;
+    int l2_cfg;
     int l2_HP, l2_S_ci, l2_S_h, l2_S_v;
     size_t l2_smem_ci, l2_smem_h, l2_smem_v;
 };
 
-constexpr int kL2B = 6, kL2NW = 16;        // loaded-tile passes: 16 consumer warps, 6 outputs per block
-constexpr int kL2BCi = 8, kL2NWCi = 12;    // pass 1 (tiles are computed): 12 consumer warps, 8 outputs per block
+// k_line2 configurations (consumer warps NW, outputs per block B, ring stages NS, outputs per tile ~ NW * B):
+//   cfg 0: loaded-tile passes 16 x 6, 3 stages of ~96 outputs;  pass 1 (tiles are computed) 12 x 8, 3 stages
+//   cfg 1: every pass 16 x 4, 4 stages of ~64 outputs (one more tile in flight, shorter blocks)
+struct L2Cfg { int NW, B, NS; };
+static const L2Cfg kL2Cfg[2][2] = {{{16, 6, 3}, {12, 8, 3}}, {{16, 4, 4}, {16, 4, 4}}};  // [cfg][0 loaded, 1 computed]
 
-// outputs per tile along a line of `len` outputs: close to 96, a multiple of the block size, the line cut evenly
-static int line2_segment(int len, int B)
+// outputs per tile along a line of `len` outputs: close to NW * B, a multiple of the block size, the line cut evenly
+static int line2_segment(int len, int B, int NW)
 {
-    const int nseg = (len + 95) / 96;
+    const int full = NW * B;
+    const int nseg = (len + full - 1) / full;
     int S = (len + nseg - 1) / nseg;
     S = ((S + B - 1) / B) * B;
     return S < B ? B : S;
@@ -192,9 +197,8 @@ static int pick_line_segment(int len, int halo, int LP, bool ci, size_t *smem_ou
     return 0;
 }
 
-static int make_plan(CostPlan &pl, int H, int W, int D, int zd, int usd, int sm_count)
+static int make_plan(CostPlan &pl, int H, int W, int D, int zd, int usd, int l2_cfg)
 {
-    (void)sm_count;
     if (D < 1 || zd < 0 || zd > D || usd < 0 || usd > 64) return fail(S2MV_ERR_BAD_PARAM, "num_disp/zero_disp/usd out of range");
     pl.D = D;
     pl.usd = usd;
@@ -225,13 +229,15 @@ static int make_plan(CostPlan &pl, int H, int W, int D, int zd, int usd, int sm_
     // persistent pipelined line kernel: one warp per pixel (128 disparities per chunk), three tiles per SM
     pl.line2 = false;
     if (pl.LP == 32) {
+        pl.l2_cfg = l2_cfg;
+        const L2Cfg &ld = kL2Cfg[l2_cfg][0], &ci = kL2Cfg[l2_cfg][1];
         pl.l2_HP = (usd + 1) & ~1;
-        pl.l2_S_ci = line2_segment(W, kL2BCi);
-        pl.l2_S_h = line2_segment(W, kL2B);
-        pl.l2_S_v = line2_segment(H, kL2B);
-        pl.l2_smem_ci = line2_smem_bytes(pl.l2_S_ci, pl.l2_HP, kL2BCi, true);
-        pl.l2_smem_h = line2_smem_bytes(pl.l2_S_h, pl.l2_HP, kL2B, false);
-        pl.l2_smem_v = line2_smem_bytes(pl.l2_S_v, pl.l2_HP, kL2B, false);
+        pl.l2_S_ci = line2_segment(W, ci.B, ci.NW);
+        pl.l2_S_h = line2_segment(W, ld.B, ld.NW);
+        pl.l2_S_v = line2_segment(H, ld.B, ld.NW);
+        pl.l2_smem_ci = line2_smem_bytes(pl.l2_S_ci, pl.l2_HP, ci.B, true, ci.NS);
+        pl.l2_smem_h = line2_smem_bytes(pl.l2_S_h, pl.l2_HP, ld.B, false, ld.NS);
+        pl.l2_smem_v = line2_smem_bytes(pl.l2_S_v, pl.l2_HP, ld.B, false, ld.NS);
         const size_t cap = 227 * 1024;
         pl.line2 = pl.l2_smem_ci <= cap && pl.l2_smem_h <= cap && pl.l2_smem_v <= cap;
     }
@@ -319,6 +325,7 @@ struct s2mv_ctx {
     int env_irv_dense_min = -1;     // S2MV_IRV_DENSE_MIN (-1: not set)
     bool env_bilateral_scalar = false;  // S2MV_BILATERAL_SCALAR
     bool env_line_v1 = false;           // S2MV_LINE_V1: the first form of the cost-volume kernel (k_line) for every plan
+    int env_l2_cfg = 0;                 // S2MV_L2_CFG: k_line2 configuration (kL2Cfg)
     bool env_line_bulk = false;         // S2MV_LINE_BULK: k_line2 with per-position bulk copies instead of the tensor map
     int *line_ctr = nullptr;            // k_line2 work counters, one per pass
     CUtensorMap tmap_vol[2][2];         // tensor maps of the ping-pong volumes: [buffer A/B][row tile / column tile]
@@ -418,6 +425,7 @@ extern "C" int s2mv_create(s2mv_ctx **out, int device)
     if (const char *e = getenv("S2MV_IRV_DENSE_MIN")) c->env_irv_dense_min = atoi(e) < 0 ? 0 : atoi(e);
     if (const char *e = getenv("S2MV_BILATERAL_SCALAR")) c->env_bilateral_scalar = atoi(e) != 0;
     if (const char *e = getenv("S2MV_LINE_V1")) c->env_line_v1 = atoi(e) != 0;
+    if (const char *e = getenv("S2MV_L2_CFG")) c->env_l2_cfg = atoi(e) == 1 ? 1 : 0;
     if (const char *e = getenv("S2MV_LINE_BULK")) c->env_line_bulk = atoi(e) != 0;
     if (const char *e = getenv("S2MV_BAND_WAIT_SPINS")) c->env_band_wait_spins = atoll(e) > 0 ? atoll(e) : 1;
     c->device = device;
@@ -474,6 +482,16 @@ static int set_line_attrs()
     return S2MV_OK;
 }
 
+template <int NW, int B, int NS>
+static int set_line2_attrs()
+{
+    const size_t big = 227 * 1024;
+    TRY((set_smem(k_line2<LM_H, NW, B, NS>, big)));
+    TRY((set_smem(k_line2<LM_H_WTA, NW, B, NS>, big)));
+    TRY((set_smem(k_line2<LM_V, NW, B, NS>, big)));
+    return S2MV_OK;
+}
+
 static int set_kernel_attrs()
 {
     const size_t big = 227 * 1024;
@@ -486,10 +504,10 @@ static int set_kernel_attrs()
     TRY(set_line_attrs<8>());
     TRY(set_line_attrs<16>());
     TRY(set_line_attrs<32>());
-    TRY(set_smem(k_line2<LM_CI_H, kL2NWCi, kL2BCi>, big));
-    TRY(set_smem(k_line2<LM_H, kL2NW, kL2B>, big));
-    TRY(set_smem(k_line2<LM_H_WTA, kL2NW, kL2B>, big));
-    TRY(set_smem(k_line2<LM_V, kL2NW, kL2B>, big));
+    TRY((set_smem(k_line2<LM_CI_H, 12, 8, 3>, big)));
+    TRY((set_smem(k_line2<LM_CI_H, 16, 4, 4>, big)));
+    TRY((set_line2_attrs<16, 6, 3>()));
+    TRY((set_line2_attrs<16, 4, 4>()));
     TRY(set_smem(k_bilateral, 160 * 1024));
     TRY(set_smem(k_bilateral4<7, true>, 64 * 1024));
     TRY(set_smem(k_bilateral4<7, false>, 64 * 1024));
@@ -606,7 +624,7 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     CostPlan pl;
-    TRY(make_plan(pl, p->num_rows, p->num_cols, p->num_disp, p->zero_disp, p->usd, c->sm_count));
+    TRY(make_plan(pl, p->num_rows, p->num_cols, p->num_disp, p->zero_disp, p->usd, c->env_l2_cfg));
     {   // interlace geometry (d_mux_multiview.cu:146): must not divide by zero later (Q27)
         float yi = (float)((double)(float)p->num_views / tan((double)((float)p->angle * 3.1415926535f) / 180.0) / (double)(float)p->elem_sz);
         if (!(fabsf(yi) < 1e9f) || (int)roundf(yi) == 0)
@@ -866,7 +884,7 @@ static int launch_pass(s2mv_ctx *c, LineArgs a, int pass, float4 *A, float4 *B, 
         L.P = L.S + 2 * L.HP;
         const int len = vert ? rows : W;
         L.tiles_per_line = (len + L.S - 1) / L.S;
-        L.claims_per_line = vert ? 1 : std::max(1, (L.tiles_per_line + 5) / 10);
+        L.claims_per_line = vert ? 1 : std::max(1, (L.tiles_per_line + 7) / 15);
         L.tiles_per_claim = (L.tiles_per_line + L.claims_per_line - 1) / L.claims_per_line;
         L.nlines = vert ? W : rows;
         L.nz = nviews * a.nchunks;
@@ -882,10 +900,21 @@ static int launch_pass(s2mv_ctx *c, LineArgs a, int pass, float4 *A, float4 *B, 
         const CUtensorMap &tm = c->tmap_vol[src_buf][vert ? 1 : 0];
         CU(cudaMemsetAsync(L.counter, 0, sizeof(int), st));
         const int grid = std::min(c->sm_count, L.nclaims);
-        if (ci) k_line2<LM_CI_H, kL2NWCi, kL2BCi><<<grid, (kL2NWCi + 1) * 32, pl.l2_smem_ci, st>>>(L, tm);
-        else if (vert) k_line2<LM_V, kL2NW, kL2B><<<grid, (kL2NW + 1) * 32, pl.l2_smem_v, st>>>(L, tm);
-        else if (pass == 4 && to_wta) k_line2<LM_H_WTA, kL2NW, kL2B><<<grid, (kL2NW + 1) * 32, pl.l2_smem_h, st>>>(L, tm);
-        else k_line2<LM_H, kL2NW, kL2B><<<grid, (kL2NW + 1) * 32, pl.l2_smem_h, st>>>(L, tm);
+        const int mode = ci ? LM_CI_H : (vert ? LM_V : ((pass == 4 && to_wta) ? LM_H_WTA : LM_H));
+        const size_t smem = ci ? pl.l2_smem_ci : (vert ? pl.l2_smem_v : pl.l2_smem_h);
+#define S2MV_L2_LAUNCH(MODE, NW, B, NS) k_line2<MODE, NW, B, NS><<<grid, (NW + kL2Producers) * 32, smem, st>>>(L, tm)
+        if (pl.l2_cfg == 0) {
+            if (mode == LM_CI_H) S2MV_L2_LAUNCH(LM_CI_H, 12, 8, 3);
+            else if (mode == LM_V) S2MV_L2_LAUNCH(LM_V, 16, 6, 3);
+            else if (mode == LM_H_WTA) S2MV_L2_LAUNCH(LM_H_WTA, 16, 6, 3);
+            else S2MV_L2_LAUNCH(LM_H, 16, 6, 3);
+        } else {
+            if (mode == LM_CI_H) S2MV_L2_LAUNCH(LM_CI_H, 16, 4, 4);
+            else if (mode == LM_V) S2MV_L2_LAUNCH(LM_V, 16, 4, 4);
+            else if (mode == LM_H_WTA) S2MV_L2_LAUNCH(LM_H_WTA, 16, 4, 4);
+            else S2MV_L2_LAUNCH(LM_H, 16, 4, 4);
+        }
+#undef S2MV_L2_LAUNCH
         KCHECK();
         c->launches += 1;
         return S2MV_OK;
