@@ -582,4 +582,255 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
     }
 }
 
+
+// =====================================================================================================
+// k_line_vv — the two vertical passes (V2 and V3 of H, V, V, H; d_ca_cross.cu:261-264) in ONE kernel: the
+// volume between them never exists in HBM (the separate passes move 4V per view for it, this one 2V).
+//
+// Both passes sum along the same column with the SAME windows (same pixel, same up/down arms):
+//     V2[r] = sum_{k in [r-U_r, r+D_r)} H1[k]        V3[r] = sum_{k in [r-U_r, r+D_r)} V2[k]
+// A CTA walks down a column in tiles of S rows.  Step j:
+//   * the producer warps fetch H1 rows [jS, jS + S + 2u) with one tensor copy (ring of three stages) and build
+//     the window masks of the row blocks that become computable (each row block's masks serve both passes);
+//   * the A warps (one block of B rows each) compute V2 for the S NEW rows [jS+u, jS+S+u) into the V2 buffer of
+//     the step, after copying the 2u rows that buffer shares with the previous step's (shared memory to shared
+//     memory: no V2 row is ever computed twice); at the top of a column they also compute rows [0, u);
+//   * the B warps compute V3 for rows [jS, jS+S) from that V2 buffer (rows [jS-u, jS+S+u)) and store them.
+// A runs one step ahead of B (two V2 buffers); "V2 of step n complete" and "V3 of step n complete" are
+// mbarriers.  Every accumulator receives exactly the reference's additions in the reference's order
+// (d_ca_cross_sum.cu:148-198), so the result equals the two separate passes bit for bit.
+struct LineVVArgs {
+    LineArgs a;           // in = H1 volume (unused when the tensor map is), out = V3 volume, arms
+    int S, HP, P;         // rows per tile, halo rows (>= usd, a multiple of B), S + 2*HP
+    int tiles_per_col, ncols, nz, nclaims;
+    int *counter;
+};
+
+struct LineVVDesc {
+    int valid, col, vslot, chunk, j, colbase, pad0, pad1;
+};
+
+constexpr int kVVMaskRing = 64;  // row blocks whose masks are kept
+
+template <int NA, int B>
+__host__ __device__ inline size_t linevv_smem_bytes(int S, int HP)
+{
+    const size_t P = (size_t)S + 2 * HP;
+    size_t b = 128 + 5 * P * kL2PosBytes;                                         // 3 H1 stages + 2 V2 buffers
+    b += 128;                                                                     // mbarriers
+    b += line2_align16(kL2DescRing * sizeof(LineVVDesc));
+    b += line2_align16((size_t)kVVMaskRing * line2_frame(B, HP) * 2);             // masks
+    b += line2_align16((size_t)kVVMaskRing * 4);                                  // bounds
+    b += kL2DescRing * 4;                                                         // claimed columns
+    return b;
+}
+
+template <int NA, int B>
+__global__ void __launch_bounds__((2 * NA + kL2Producers) * 32, 1)
+k_line_vv(const __grid_constant__ LineVVArgs L, const __grid_constant__ CUtensorMap tmap)
+{
+    extern __shared__ __align__(16) unsigned char smem_l2[];
+    const LineArgs &a = L.a;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = L.S, HP = L.HP, P = L.P, W = a.W, H = a.H;
+    const int NBS = S / B, NBH = HP / B;  // row blocks per tile / per halo
+
+    unsigned char *smem_raw = smem_l2 + ((128u - (smem_u32(smem_l2) & 127u)) & 127u);
+    const uint32_t tile_bytes = (uint32_t)P * kL2PosBytes;
+    const uint32_t h1_base = smem_u32(smem_raw), v2_base = h1_base + 3u * tile_bytes;
+    unsigned char *sp = smem_raw + 5 * (size_t)tile_bytes;
+    const uint32_t bars = smem_u32(sp);  // fullH[3] emptyH[3] v2done[2] v3done[2]
+    sp += 128;
+    LineVVDesc *desc = reinterpret_cast<LineVVDesc *>(sp);
+    sp += line2_align16(kL2DescRing * sizeof(LineVVDesc));
+    const int FR = line2_frame(B, HP);
+    uint16_t *sMask = reinterpret_cast<uint16_t *>(sp);
+    sp += line2_align16((size_t)kVVMaskRing * FR * 2);
+    uint32_t *sBounds = reinterpret_cast<uint32_t *>(sp);
+    sp += line2_align16((size_t)kVVMaskRing * 4);
+    volatile int *sClaim = reinterpret_cast<volatile int *>(sp);
+
+    auto fullH = [&](int s) { return bars + 8u * s; };
+    auto emptyH = [&](int s) { return bars + 8u * (3 + s); };
+    auto v2done = [&](int s) { return bars + 8u * (6 + s); };
+    auto v3done = [&](int s) { return bars + 8u * (8 + s); };
+
+    if (tid == 0) {
+        for (int s = 0; s < 3; ++s) {
+            mbar_init(fullH(s), 32 * kL2Producers + 1);
+            mbar_init(emptyH(s), NA);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(v2done(s), NA);
+            mbar_init(v3done(s), NA);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // =========================================================== producer warps
+    if (warp >= 2 * NA) {
+        const int pw = warp - 2 * NA;
+        int j = 0, jend = 0, col = 0, vslot = 0, chunk = 0, nclaim = 0, colbase = 0, nextbase = 0;
+        for (int n = 0;; ++n) {
+            const int st = n % 3, ring = n % kL2DescRing;
+            if (n >= 3) mbar_wait(emptyH(st), ((n / 3) - 1) & 1);
+            int valid = 1;
+            if (j == jend) {  // next column
+                int c = 0;
+                if (pw == 0) {
+                    if (lane == 0) {
+                        c = atomicAdd(L.counter, 1);
+                        sClaim[nclaim % kL2DescRing] = c;
+                    }
+                    __syncwarp();
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kL2Producers) : "memory");
+                c = sClaim[nclaim % kL2DescRing];
+                ++nclaim;
+                if (c >= L.nclaims) {
+                    valid = 0;
+                } else {
+                    const int z = c / L.ncols;
+                    col = c - z * L.ncols;
+                    vslot = z / a.nchunks;
+                    chunk = z - vslot * a.nchunks;
+                    j = 0;
+                    jend = L.tiles_per_col;
+                    colbase = nextbase;
+                    nextbase = (nextbase + NBH + NBS * L.tiles_per_col) % kVVMaskRing;
+                }
+            }
+            if (pw == 0 && lane == 0) {
+                LineVVDesc d;
+                d.valid = valid; d.col = col; d.vslot = vslot; d.chunk = chunk; d.j = j; d.colbase = colbase; d.pad0 = d.pad1 = 0;
+                desc[ring] = d;
+                if (valid) {
+                    mbar_arrive_expect_tx(fullH(st), tile_bytes);
+                    tma_load_4d(h1_base + (uint32_t)st * tile_bytes, &tmap, chunk * 128, col, j * S, vslot, fullH(st));
+                } else {
+                    mbar_arrive_expect_tx(fullH(st), 0u);
+                }
+            }
+            if (valid) {
+                // masks of the row blocks that become computable at this step: g = NBH + j*NBS + i (rows
+                // [jS + HP + B*i, +B)), i < NBS; at the top of a column also g = 0..NBH-1 (rows [0, HP))
+                const int nb = NBS + (j == 0 ? NBH : 0);
+                const int g0 = j == 0 ? 0 : NBH + j * NBS;
+                const int FRl = FR, PL = (FR + 7) / 8, slice = lane & 7;
+                for (int i = pw * 4 + (lane >> 3); i < nb; i += 4 * kL2Producers) {
+                    const int g = g0 + i, r0 = g * B, slot = (colbase + g) % kVVMaskRing;
+                    uint32_t s_rel[B], len[B];
+                    int first = 0x7fffffff, end = 0;
+#pragma unroll
+                    for (int k = 0; k < B; ++k) {
+                        const int r = r0 + k;
+                        uint32_t ar = 0u;
+                        if (r < H) ar = __ldg(a.arms[vslot] + (size_t)r * W + col);
+                        const int A = arm_up(ar), Bn = arm_down(ar);
+                        s_rel[k] = (uint32_t)(k + HP - A);
+                        len[k] = (uint32_t)(A + Bn);
+                        if (A + Bn > 0) {
+                            first = min(first, k + HP - A);
+                            end = max(end, k + HP + Bn);
+                        }
+                    }
+                    uint16_t *mrow = sMask + (size_t)slot * FRl;
+                    const int k1 = min(FRl, (slice + 1) * PL);
+                    for (int k = slice * PL; k < k1; ++k) {
+                        uint32_t m = 0;
+#pragma unroll
+                        for (int q = 0; q < B; ++q) m |= (((uint32_t)k - s_rel[q]) < len[q]) ? (2u << q) : 0u;
+                        mrow[k] = (uint16_t)m;
+                    }
+                    if (slice == 0) sBounds[slot] = end > 0 ? ((uint32_t)first | ((uint32_t)end << 16)) : 0u;
+                }
+            }
+            mbar_arrive(fullH(st));
+            if (!valid) break;
+            ++j;
+        }
+        return;
+    }
+
+    const bool isA = warp < NA;
+    const int w = isA ? warp : warp - NA;
+    const uint32_t lane16 = (uint32_t)lane * 16u;
+
+    if (isA) {
+        // =========================================================== A warps: V2 = V(H1)
+        for (int n = 0;; ++n) {
+            const int st = n % 3, vb = n & 1;
+            mbar_wait(fullH(st), (n / 3) & 1);
+            const LineVVDesc d = desc[n % kL2DescRing];
+            if (n >= 1) mbar_wait(v2done(vb ^ 1), ((n - 1) >> 1) & 1);  // the previous step's V2 rows (carry source)
+            if (n >= 2) mbar_wait(v3done(vb), ((n - 2) >> 1) & 1);      // this V2 buffer's last readers
+            if (!d.valid) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(v2done(vb));
+                break;
+            }
+            const uint32_t h1 = h1_base + (uint32_t)st * tile_bytes + lane16;     // position 0 = row jS
+            const uint32_t v2 = v2_base + (uint32_t)vb * tile_bytes + lane16;     // position 0 = row jS - HP
+            if (d.j > 0) {
+                // rows [jS - HP, jS + HP) were computed by the previous step: its positions [S, S + 2*HP)
+                const uint32_t src = v2_base + (uint32_t)(vb ^ 1) * tile_bytes + lane16 + (uint32_t)S * kL2PosBytes;
+                for (int p = w; p < 2 * HP; p += NA) {
+                    const float4 v = lds128<0>(src + (uint32_t)p * kL2PosBytes);
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(v2 + (uint32_t)p * kL2PosBytes), "f"(v.x), "f"(v.y),
+                                 "f"(v.z), "f"(v.w)
+                                 : "memory");
+                }
+            }
+            // new rows: blocks i < NBS are rows [jS + HP + B*i, +B) = row blocks g = NBH + j*NBS + i; at the top
+            // of a column blocks NBS.. are rows [0, HP) = g = 0..NBH-1
+            const int nb = NBS + (d.j == 0 ? NBH : 0);
+            for (int i = w; i < nb; i += NA) {
+                const int g = i < NBS ? NBH + d.j * NBS + i : i - NBS;
+                const int slot = (d.colbase + g) % kVVMaskRing;
+                const int r0 = g * B;                       // first row of the block
+                // frame position 0 = row r0 - HP = H1 tile position r0 - HP - jS
+                float4 acc[B];
+                sum_block_masked<B>(h1, smem_u32(sMask + (size_t)slot * FR), sBounds[slot], r0 - HP - d.j * S, acc);
+                const uint32_t dst = v2 + (uint32_t)(r0 - d.j * S + HP) * kL2PosBytes;  // V2 buffer position of row r0
+#pragma unroll
+                for (int k = 0; k < B; ++k)
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst + (uint32_t)k * kL2PosBytes), "f"(acc[k].x),
+                                 "f"(acc[k].y), "f"(acc[k].z), "f"(acc[k].w)
+                                 : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(emptyH(st));
+                mbar_arrive(v2done(vb));
+            }
+        }
+    } else {
+        // =========================================================== B warps: V3 = V(V2), stored
+        const long long ostride = (long long)W * a.LPtot * 16;  // bytes between rows of a column
+        for (int n = 0;; ++n) {
+            const int vb = n & 1;
+            mbar_wait(v2done(vb), (n >> 1) & 1);
+            const LineVVDesc d = desc[n % kL2DescRing];
+            if (!d.valid) break;
+            const uint32_t v2 = v2_base + (uint32_t)vb * tile_bytes + lane16;  // position 0 = row jS - HP
+            char *colp = reinterpret_cast<char *>(a.out[d.vslot] + (size_t)d.col * a.LPtot + (size_t)d.chunk * 32 + lane);
+            for (int i = w; i < NBS; i += NA) {
+                const int g = d.j * NBS + i, r0 = g * B;
+                if (r0 >= H) break;
+                const int slot = (d.colbase + g) % kVVMaskRing;
+                // frame position 0 = row r0 - HP = V2 buffer position r0 - jS
+                float4 acc[B];
+                sum_block_masked<B>(v2, smem_u32(sMask + (size_t)slot * FR), sBounds[slot], r0 - d.j * S, acc);
+                char *dstp = colp + (long long)r0 * ostride;
+#pragma unroll
+                for (int k = 0; k < B; ++k)
+                    if (r0 + k < H) *reinterpret_cast<float4 *>(dstp + k * ostride) = acc[k];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(v3done(vb));
+        }
+    }
+}
+
 }  // namespace s2mv

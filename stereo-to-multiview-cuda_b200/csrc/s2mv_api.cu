@@ -130,11 +130,16 @@ struct CostPlan {
     int l2_cfg;
     int l2_HP, l2_S_ci, l2_S_h, l2_S_v;
     size_t l2_smem_ci, l2_smem_h, l2_smem_v;
+    // k_line_vv (the two vertical passes fused): rows per tile, halo rows, shared memory; vv = usable
+    bool vv;
+    int vv_S, vv_HP;
+    size_t vv_smem;
 };
 
 // k_line2 configurations (consumer warps NW, outputs per block B, ring stages NS, outputs per tile ~ NW * B):
 //   cfg 0: loaded-tile passes 16 x 6, 3 stages of ~96 outputs;  pass 1 (tiles are computed) 12 x 8, 3 stages
 //   cfg 1: every pass 16 x 4, 4 stages of ~64 outputs (one more tile in flight, shorter blocks)
+constexpr int kVVNA = 8, kVVB = 6;   // k_line_vv: 8 + 8 consumer warps, 6 rows per block, 48 rows per tile
 struct L2Cfg { int NW, B, NS; };
 static const L2Cfg kL2Cfg[2][2] = {{{16, 6, 3}, {12, 8, 3}}, {{16, 4, 4}, {16, 4, 4}}};  // [cfg][0 loaded, 1 computed]
 
@@ -228,6 +233,7 @@ static int make_plan(CostPlan &pl, int H, int W, int D, int zd, int usd, int l2_
     if (!pl.S_h || !pl.S_v || !pl.S_h4) return fail(S2MV_ERR_BAD_PARAM, "usd too large for the shared-memory tile");
     // persistent pipelined line kernel: one warp per pixel (128 disparities per chunk), three tiles per SM
     pl.line2 = false;
+    pl.vv = false;
     if (pl.LP == 32) {
         pl.l2_cfg = l2_cfg;
         const L2Cfg &ld = kL2Cfg[l2_cfg][0], &ci = kL2Cfg[l2_cfg][1];
@@ -240,6 +246,11 @@ static int make_plan(CostPlan &pl, int H, int W, int D, int zd, int usd, int l2_
         pl.l2_smem_v = line2_smem_bytes(pl.l2_S_v, pl.l2_HP, ld.B, false, ld.NS);
         const size_t cap = 227 * 1024;
         pl.line2 = pl.l2_smem_ci <= cap && pl.l2_smem_h <= cap && pl.l2_smem_v <= cap;
+        pl.vv_HP = ((usd + kVVB - 1) / kVVB) * kVVB;
+        if (pl.vv_HP < kVVB) pl.vv_HP = kVVB;
+        pl.vv_S = kVVNA * kVVB;
+        pl.vv_smem = linevv_smem_bytes<kVVNA, kVVB>(pl.vv_S, pl.vv_HP);
+        pl.vv = pl.line2 && pl.vv_smem <= cap;
     }
     return S2MV_OK;
 }
@@ -329,6 +340,8 @@ struct s2mv_ctx {
     bool env_line_bulk = false;         // S2MV_LINE_BULK: k_line2 with per-position bulk copies instead of the tensor map
     int *line_ctr = nullptr;            // k_line2 work counters, one per pass
     CUtensorMap tmap_vol[2][2];         // tensor maps of the ping-pong volumes: [buffer A/B][row tile / column tile]
+    CUtensorMap tmap_vv;                // buffer A, column tile of the fused vertical passes
+    bool env_no_vv = false;             // S2MV_NO_VV: run the vertical passes as two launches
     bool tmap_ok = false;
     long long env_band_wait_spins = 20000000;  // S2MV_BAND_WAIT_SPINS: probes (1 us apart) before a halo wait gives up
     cudaEvent_t ev_refined = nullptr;   // disparities final (before DIBR): the synchronous call starts their D2H here
@@ -426,6 +439,7 @@ extern "C" int s2mv_create(s2mv_ctx **out, int device)
     if (const char *e = getenv("S2MV_BILATERAL_SCALAR")) c->env_bilateral_scalar = atoi(e) != 0;
     if (const char *e = getenv("S2MV_LINE_V1")) c->env_line_v1 = atoi(e) != 0;
     if (const char *e = getenv("S2MV_L2_CFG")) c->env_l2_cfg = atoi(e) == 1 ? 1 : 0;
+    if (const char *e = getenv("S2MV_NO_VV")) c->env_no_vv = atoi(e) != 0;
     if (const char *e = getenv("S2MV_LINE_BULK")) c->env_line_bulk = atoi(e) != 0;
     if (const char *e = getenv("S2MV_BAND_WAIT_SPINS")) c->env_band_wait_spins = atoll(e) > 0 ? atoll(e) : 1;
     c->device = device;
@@ -504,6 +518,7 @@ static int set_kernel_attrs()
     TRY(set_line_attrs<8>());
     TRY(set_line_attrs<16>());
     TRY(set_line_attrs<32>());
+    TRY((set_smem(k_line_vv<kVVNA, kVVB>, big)));
     TRY((set_smem(k_line2<LM_CI_H, 12, 8, 3>, big)));
     TRY((set_smem(k_line2<LM_CI_H, 16, 4, 4>, big)));
     TRY((set_line2_attrs<16, 6, 3>()));
@@ -607,6 +622,12 @@ static bool make_volume_tmaps(s2mv_ctx *c, size_t vol_rows)
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return false;
         }
+    if (pl.vv) {
+        const cuuint32_t box[4] = {128, 1, (cuuint32_t)(pl.vv_S + 2 * pl.vv_HP), 1};
+        CUresult r = enc(&c->tmap_vv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->vol[0], gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return false;
+    }
     return true;
 }
 
@@ -953,6 +974,29 @@ static int launch_aggregate(s2mv_ctx *c, const LineArgs &a, float4 *A, float4 *B
     return S2MV_OK;
 }
 
+// The two vertical passes in one launch (k_line_vv): reads volume buffer A (pass 1's output) through its tensor map,
+// writes buffer B.  Whole-frame contexts only (a row band exchanges pass 2's output with its neighbours).
+static int launch_vv(s2mv_ctx *c, LineArgs a, float4 *Bout, size_t view_stride4, int nviews, cudaStream_t st)
+{
+    const CostPlan &pl = c->plan;
+    LineVVArgs L;
+    memset(&L, 0, sizeof(L));
+    for (int v = 0; v < nviews; ++v) a.out[v] = Bout + v * view_stride4;
+    L.a = a;
+    L.S = pl.vv_S; L.HP = pl.vv_HP; L.P = L.S + 2 * L.HP;
+    L.tiles_per_col = (a.H + L.S - 1) / L.S;
+    L.ncols = a.W;
+    L.nz = nviews * a.nchunks;
+    L.nclaims = L.nz * L.ncols;
+    L.counter = c->line_ctr + 5;
+    CU(cudaMemsetAsync(L.counter, 0, sizeof(int), st));
+    const int grid = std::min(c->sm_count, L.nclaims);
+    k_line_vv<kVVNA, kVVB><<<grid, (2 * kVVNA + kL2Producers) * 32, pl.vv_smem, st>>>(L, c->tmap_vv);
+    KCHECK();
+    c->launches += 1;
+    return S2MV_OK;
+}
+
 // Four-direction scanline optimisation of `nviews` aggregated volumes (slot v at cost + v * view_stride4)
 // into acc (same layout), then WTA into disp[] (kernels_so.cuh; specification: DESIGN.md §3.4, held to it by tests/test_so.py).
 static int launch_so(s2mv_ctx *c, const float4 *cost, float4 *acc, size_t view_stride4, float *const disp[2], int nviews,
@@ -1006,13 +1050,27 @@ static int launch_costvol(s2mv_ctx *c, float *dispL, float *dispR, cudaStream_t 
         TRY(launch_so(c, B, A, view_stride4, disp, 2, 0, c->so_T, c->so_H1, c->so_H2, p.num_disp, p.zero_disp, H, W, false, st));
         return S2MV_OK;
     }
+    // fused vertical passes: CI+H1 -> A, V2∘V3: A -> B, H4+WTA from B
+    const bool fused = pl.line2 && pl.vv && c->tmap_ok && !c->env_line_v1 && !c->env_line_bulk && !c->env_no_vv;
+    auto aggregate = [&](const LineArgs &aa) -> int {
+        if (!fused) return launch_aggregate(c, aa, A, B, view_stride4, 2, true, true, st);
+        const RowRange rr = {0, aa.H, 0, aa.H};
+        if (c->timing) CU(cudaEventRecord(c->kev[0], st));
+        TRY(launch_pass(c, aa, 1, A, B, view_stride4, 2, true, true, rr, st));
+        if (c->timing) CU(cudaEventRecord(c->kev[1], st));
+        TRY(launch_vv(c, aa, B, view_stride4, 2, st));
+        if (c->timing) { CU(cudaEventRecord(c->kev[2], st)); CU(cudaEventRecord(c->kev[3], st)); }
+        TRY(launch_pass(c, aa, 4, /*read*/ B, /*unused*/ A, view_stride4, 2, true, true, rr, st));
+        if (c->timing) CU(cudaEventRecord(c->kev[4], st));
+        return S2MV_OK;
+    };
     if (pl.chunk_seq) {
         for (int ch = 0; ch < pl.nchunks; ++ch) {
             a.d_first = ch * 4 * pl.LP;
-            TRY(launch_aggregate(c, a, A, B, view_stride4, 2, true, true, st));
+            TRY(aggregate(a));
         }
     } else {
-        TRY(launch_aggregate(c, a, A, B, view_stride4, 2, true, true, st));
+        TRY(aggregate(a));
     }
     if (pl.nchunks > 1) {
         k_wta_finish<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->wta_key[0], dispL, p.zero_disp, n);
