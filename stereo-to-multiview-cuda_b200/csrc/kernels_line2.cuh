@@ -52,6 +52,7 @@ struct Line2Args {
     int nclaims;          // nz * nlines * claims_per_line
     int *counter;         // work counter of this launch (zeroed by the host before the launch)
     int use_tmap;         // tiles arrive through the tensor map passed next to these arguments (else 512-byte bulk copies)
+    int tmap_rows;        // positions per tensor copy (the map's box): a tile is P / tmap_rows copies
     int row_bias;         // tensor-map row of image row r = r - row_bias (row bands: the volume starts at row v_lo)
 };
 
@@ -235,39 +236,41 @@ __device__ __forceinline__ void ci_fill_groups2(float4 *__restrict__ C4, const u
 // a warp, 8 lanes share a block and split its frame.  The first lane of a block also writes the block's walk
 // bounds (first position | end position << 16; 0 = nothing to add).
 constexpr int kL2Producers = 4;
-template <int B, bool VERT>
-__device__ __forceinline__ void build_masks(uint16_t *__restrict__ masks, uint32_t *__restrict__ bounds,
-                                            const uint32_t *__restrict__ arms, int W, int ln, int t0, int S, int Sact, int HP,
-                                            int pw, int lane)
+
+// This lane's output block of a tile of nb blocks (one block per group of 8 lanes, 16 per tile) or -1
+__device__ __forceinline__ int mask_lane_block(int pw, int lane, int nb)
 {
-    const int FR = line2_frame(B, HP), PL = (FR + 7) / 8;
-    const int slice = lane & 7;
-    for (int b = pw * 4 + (lane >> 3); b * B < S; b += 4 * kL2Producers) {
-        uint32_t s_rel[B], len[B];
-        int first = 0x7fffffff, end = 0;
+    const int i = pw * 4 + (lane >> 3);
+    return i < nb ? i : -1;
+}
+
+// Masks and walk bounds of one block from its B arm words (0 = output outside the line): this lane writes the
+// frame positions of its slice (8 lanes share a block), the first lane of the block the bounds.
+template <int B, bool VERT>
+__device__ __forceinline__ void masks_from_arms(uint16_t *__restrict__ mrow, uint32_t *__restrict__ bound, const uint32_t ar[B],
+                                                int HP, int lane)
+{
+    const int FR = line2_frame(B, HP), PL = (FR + 7) / 8, slice = lane & 7;
+    uint32_t s_rel[B], len[B];
+    int first = 0x7fffffff, end = 0;
 #pragma unroll
-        for (int i = 0; i < B; ++i) {
-            const int o = b * B + i;
-            uint32_t ar = 0u;
-            if (o < Sact) ar = __ldg(arms + (VERT ? (size_t)(t0 + o) * W + ln : (size_t)ln * W + (t0 + o)));
-            const int A = VERT ? arm_up(ar) : arm_left(ar), Bn = VERT ? arm_down(ar) : arm_right(ar);
-            s_rel[i] = (uint32_t)(i + HP - A);
-            len[i] = (uint32_t)(A + Bn);
-            if (A + Bn > 0) {
-                first = min(first, i + HP - A);
-                end = max(end, i + HP + Bn);
-            }
+    for (int i = 0; i < B; ++i) {
+        const int A = VERT ? arm_up(ar[i]) : arm_left(ar[i]), Bn = VERT ? arm_down(ar[i]) : arm_right(ar[i]);
+        s_rel[i] = (uint32_t)(i + HP - A);
+        len[i] = (uint32_t)(A + Bn);
+        if (A + Bn > 0) {
+            first = min(first, i + HP - A);
+            end = max(end, i + HP + Bn);
         }
-        uint16_t *mrow = masks + (size_t)b * FR;
-        const int k1 = min(FR, (slice + 1) * PL);
-        for (int k = slice * PL; k < k1; ++k) {
-            uint32_t m = 0;
-#pragma unroll
-            for (int i = 0; i < B; ++i) m |= (((uint32_t)k - s_rel[i]) < len[i]) ? (2u << i) : 0u;
-            mrow[k] = (uint16_t)m;
-        }
-        if (slice == 0) bounds[b] = end > 0 ? ((uint32_t)first | ((uint32_t)end << 16)) : 0u;
     }
+    const int k1 = min(FR, (slice + 1) * PL);
+    for (int k = slice * PL; k < k1; ++k) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int i = 0; i < B; ++i) m |= (((uint32_t)k - s_rel[i]) < len[i]) ? (2u << i) : 0u;
+        mrow[k] = (uint16_t)m;
+    }
+    if (slice == 0) *bound = end > 0 ? ((uint32_t)first | ((uint32_t)end << 16)) : 0u;
 }
 
 // ---------------------------------------------------------------- the window walk of one output block
@@ -281,7 +284,7 @@ __device__ __forceinline__ void sum_block_masked(uint32_t tq, uint32_t mrow, uin
     const uint32_t first = bd & 0xffffu, end = bd >> 16;
     uint32_t p = tq + ((uint32_t)o0 + first) * kL2PosBytes, mp = mrow + 2u * first;
     const uint32_t pend = tq + ((uint32_t)o0 + end) * kL2PosBytes;
-#pragma unroll 2
+#pragma unroll 4
     for (; p != pend; p += kL2PosBytes, mp += 2) {
         const float4 v = lds128<0>(p);
         const uint32_t m = lds16(mp);
@@ -389,6 +392,10 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
         const int pw = warp - NW;
         volatile int *sClaim = reinterpret_cast<volatile int *>(sp + line2_align16((size_t)NS * OPS * 4) + 80 * 4);  // [kL2DescRing]
         int seg = 0, seg_end = 0, ln = 0, vslot = 0, chunk = 0, first = 0, nclaim = 0;
+        uint32_t cur[B], pend_bar = 0;
+        int pend_ring = 0, pend_b = -1;
+#pragma unroll
+        for (int i = 0; i < B; ++i) cur[i] = 0u;
         for (int m = 0;; ++m) {
             const int st = m % NS, ring = m % kL2DescRing;
             if (m >= NS) mbar_wait(CI ? emptyO(st) : empty(st), ((m / NS) - 1) & 1);
@@ -435,8 +442,11 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
                 } else if (L.use_tmap) {
                     mbar_arrive_expect_tx(bar, tile_bytes);
                     const uint32_t dst = smem_u32(smem_raw) + (uint32_t)st * tile_bytes;
-                    if (VERT) tma_load_4d(dst, &tmap, chunk * 128, ln, t0 - HP - L.row_bias, vslot, bar);
-                    else tma_load_4d(dst, &tmap, chunk * 128, t0 - HP, ln - L.row_bias, vslot, bar);
+                    // several copies per tile: more requests of the copy engine in flight
+                    for (int p0 = 0; p0 < P; p0 += L.tmap_rows) {
+                        if (VERT) tma_load_4d(dst + (uint32_t)p0 * kL2PosBytes, &tmap, chunk * 128, ln, t0 - HP - L.row_bias + p0, vslot, bar);
+                        else tma_load_4d(dst + (uint32_t)p0 * kL2PosBytes, &tmap, chunk * 128, t0 - HP + p0, ln - L.row_bias, vslot, bar);
+                    }
                 }
             }
             if (!CI && valid && !L.use_tmap && pw == 0) {
@@ -451,37 +461,54 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
                 for (int p = lane; p < np; p += 32)
                     bulk_g2s(dst0 + (uint32_t)p * kL2PosBytes, src0 + (long long)p * gs, kL2PosBytes, bar);
             }
-            if (valid) {
-                if (CI) {
-                    const int view = a.view_first + vslot;
-                    const int d0 = a.d_first + chunk * 128;
-                    const size_t row = (size_t)ln * W;
-                    const int xb = t0 - HP;
-                    // other-view words start at the column that makes every thread's 8-word window 16-byte aligned
-                    const int xo = (view == 0) ? (xb - a.zd + d0) : (xb + a.zd - d0 - 128);
-                    const uint32_t *gOwnP = (view == 0 ? a.pixL : a.pixR) + row, *gOwnC = (view == 0 ? a.cenL : a.cenR) + row;
-                    const uint32_t *gOthP = (view == 0 ? a.pixR : a.pixL) + row, *gOthC = (view == 0 ? a.cenR : a.cenL) + row;
-                    const uint32_t o0 = smem_u32(sOps + (size_t)st * OPS);
-                    // a continued run only needs the operands of its S new positions; the first tile all of them
-                    const int i0 = first ? 0 : 2 * HP;
-                    const int pl = pw * 32 + lane;
-                    for (int i = i0 + pl; i < P; i += 32 * kL2Producers) {
-                        const int x = clampi(xb + i, 0, W - 1);
-                        cp_async4(o0 + 4u * i, gOwnP + x, 4u);
-                        cp_async4(o0 + 4u * (P + i), gOwnC + x, 4u);
-                    }
-                    for (int i = i0 + pl; i < P + 128; i += 32 * kL2Producers) {
-                        const int x = clampi(xo + i, 0, W - 1);
-                        cp_async4(o0 + 4u * (2 * P + i), gOthP + x, 4u);
-                        cp_async4(o0 + 4u * (3 * P + 128 + i), gOthC + x, 4u);
-                    }
+            if (valid && CI) {
+                const int view = a.view_first + vslot;
+                const int d0 = a.d_first + chunk * 128;
+                const size_t row = (size_t)ln * W;
+                const int xb = t0 - HP;
+                // other-view words start at the column that makes every thread's 8-word window 16-byte aligned
+                const int xo = (view == 0) ? (xb - a.zd + d0) : (xb + a.zd - d0 - 128);
+                const uint32_t *gOwnP = (view == 0 ? a.pixL : a.pixR) + row, *gOwnC = (view == 0 ? a.cenL : a.cenR) + row;
+                const uint32_t *gOthP = (view == 0 ? a.pixR : a.pixL) + row, *gOthC = (view == 0 ? a.cenR : a.cenL) + row;
+                const uint32_t o0 = smem_u32(sOps + (size_t)st * OPS);
+                // a continued run only needs the operands of its S new positions; the first tile all of them
+                const int i0 = first ? 0 : 2 * HP;
+                const int pl = pw * 32 + lane;
+                for (int i = i0 + pl; i < P; i += 32 * kL2Producers) {
+                    const int x = clampi(xb + i, 0, W - 1);
+                    cp_async4(o0 + 4u * i, gOwnP + x, 4u);
+                    cp_async4(o0 + 4u * (P + i), gOwnC + x, 4u);
                 }
-                build_masks<B, VERT>(sMask + (size_t)ring * kL2MaxBlocks * FR, sBounds + ring * kL2MaxBlocks, a.arms[vslot], W, ln, t0,
-                                     S, Sact, HP, pw, lane);
+                for (int i = i0 + pl; i < P + 128; i += 32 * kL2Producers) {
+                    const int x = clampi(xo + i, 0, W - 1);
+                    cp_async4(o0 + 4u * (2 * P + i), gOthP + x, 4u);
+                    cp_async4(o0 + 4u * (3 * P + 128 + i), gOthC + x, 4u);
+                }
             }
             if (CI) cp_async_arrive_noinc(bar);
-            mbar_arrive(bar);  // releases this lane's masks (lane 0: and the descriptor)
-            if (!valid) break;
+            // Window masks, one tile behind: the arm words of THIS tile are requested now and turned into masks in
+            // the next trip, so their load latency never sits between two tiles.
+            uint32_t nxt[B];
+            const int my_b = valid ? mask_lane_block(pw, lane, S / B) : -1;
+#pragma unroll
+            for (int i = 0; i < B; ++i) {
+                const int o = my_b * B + i;
+                nxt[i] = 0u;
+                if (my_b >= 0 && o < Sact) nxt[i] = __ldg(a.arms[vslot] + (VERT ? (size_t)(t0 + o) * W + ln : (size_t)ln * W + (t0 + o)));
+            }
+            if (pend_bar) {
+                if (pend_b >= 0)
+                    masks_from_arms<B, VERT>(sMask + ((size_t)pend_ring * kL2MaxBlocks + pend_b) * FR, sBounds + pend_ring * kL2MaxBlocks + pend_b,
+                                             cur, HP, lane);
+                mbar_arrive(pend_bar);  // releases this lane's masks (leader lane 0: and the descriptor)
+            }
+#pragma unroll
+            for (int i = 0; i < B; ++i) cur[i] = nxt[i];
+            pend_bar = bar; pend_ring = ring; pend_b = my_b;
+            if (!valid) {
+                mbar_arrive(bar);
+                break;
+            }
             ++seg;
             first = 0;
         }
@@ -604,6 +631,7 @@ struct LineVVArgs {
     int S, HP, P;         // rows per tile, halo rows (>= usd, a multiple of B), S + 2*HP
     int tiles_per_col, ncols, nz, nclaims;
     int *counter;
+    int tmap_rows;        // rows per tensor copy (the map's box): a tile is P / tmap_rows copies
 };
 
 struct LineVVDesc {
@@ -672,6 +700,10 @@ k_line_vv(const __grid_constant__ LineVVArgs L, const __grid_constant__ CUtensor
     if (warp >= 2 * NA) {
         const int pw = warp - 2 * NA;
         int j = 0, jend = 0, col = 0, vslot = 0, chunk = 0, nclaim = 0, colbase = 0, nextbase = 0;
+        uint32_t cur[B], pend_bar = 0;
+        int pend_slot = -1;
+#pragma unroll
+        for (int k = 0; k < B; ++k) cur[k] = 0u;
         for (int n = 0;; ++n) {
             const int st = n % 3, ring = n % kL2DescRing;
             if (n >= 3) mbar_wait(emptyH(st), ((n / 3) - 1) & 1);
@@ -707,47 +739,41 @@ k_line_vv(const __grid_constant__ LineVVArgs L, const __grid_constant__ CUtensor
                 desc[ring] = d;
                 if (valid) {
                     mbar_arrive_expect_tx(fullH(st), tile_bytes);
-                    tma_load_4d(h1_base + (uint32_t)st * tile_bytes, &tmap, chunk * 128, col, j * S, vslot, fullH(st));
+                    for (int p0 = 0; p0 < P; p0 += L.tmap_rows)
+                        tma_load_4d(h1_base + (uint32_t)st * tile_bytes + (uint32_t)p0 * kL2PosBytes, &tmap, chunk * 128, col, j * S + p0, vslot,
+                                    fullH(st));
                 } else {
                     mbar_arrive_expect_tx(fullH(st), 0u);
                 }
             }
-            if (valid) {
-                // masks of the row blocks that become computable at this step: g = NBH + j*NBS + i (rows
-                // [jS + HP + B*i, +B)), i < NBS; at the top of a column also g = 0..NBH-1 (rows [0, HP))
-                const int nb = NBS + (j == 0 ? NBH : 0);
-                const int g0 = j == 0 ? 0 : NBH + j * NBS;
-                const int FRl = FR, PL = (FR + 7) / 8, slice = lane & 7;
-                for (int i = pw * 4 + (lane >> 3); i < nb; i += 4 * kL2Producers) {
-                    const int g = g0 + i, r0 = g * B, slot = (colbase + g) % kVVMaskRing;
-                    uint32_t s_rel[B], len[B];
-                    int first = 0x7fffffff, end = 0;
+            // Masks of the row blocks that become computable at this step: g = NBH + j*NBS + i (rows [jS + HP + B*i, +B)),
+            // i < NBS; at the top of a column also g = 0..NBH-1 (rows [0, HP)).  One block per group of 8 lanes; the arm
+            // words are requested now and turned into masks in the next trip (their latency stays off the tile cadence).
+            uint32_t nxt[B];
+            int my_slot = -1;
+            {
+                const int nb = valid ? NBS + (j == 0 ? NBH : 0) : 0;
+                const int i = mask_lane_block(pw, lane, nb);
+                const int g = (j == 0 ? 0 : NBH + j * NBS) + i;
+                if (i >= 0) my_slot = (colbase + g) % kVVMaskRing;
 #pragma unroll
-                    for (int k = 0; k < B; ++k) {
-                        const int r = r0 + k;
-                        uint32_t ar = 0u;
-                        if (r < H) ar = __ldg(a.arms[vslot] + (size_t)r * W + col);
-                        const int A = arm_up(ar), Bn = arm_down(ar);
-                        s_rel[k] = (uint32_t)(k + HP - A);
-                        len[k] = (uint32_t)(A + Bn);
-                        if (A + Bn > 0) {
-                            first = min(first, k + HP - A);
-                            end = max(end, k + HP + Bn);
-                        }
-                    }
-                    uint16_t *mrow = sMask + (size_t)slot * FRl;
-                    const int k1 = min(FRl, (slice + 1) * PL);
-                    for (int k = slice * PL; k < k1; ++k) {
-                        uint32_t m = 0;
-#pragma unroll
-                        for (int q = 0; q < B; ++q) m |= (((uint32_t)k - s_rel[q]) < len[q]) ? (2u << q) : 0u;
-                        mrow[k] = (uint16_t)m;
-                    }
-                    if (slice == 0) sBounds[slot] = end > 0 ? ((uint32_t)first | ((uint32_t)end << 16)) : 0u;
+                for (int k = 0; k < B; ++k) {
+                    const int r = g * B + k;
+                    nxt[k] = 0u;
+                    if (i >= 0 && r < H) nxt[k] = __ldg(a.arms[vslot] + (size_t)r * W + col);
                 }
             }
-            mbar_arrive(fullH(st));
-            if (!valid) break;
+            if (pend_bar) {
+                if (pend_slot >= 0) masks_from_arms<B, true>(sMask + (size_t)pend_slot * FR, sBounds + pend_slot, cur, HP, lane);
+                mbar_arrive(pend_bar);
+            }
+#pragma unroll
+            for (int k = 0; k < B; ++k) cur[k] = nxt[k];
+            pend_bar = fullH(st); pend_slot = my_slot;
+            if (!valid) {
+                mbar_arrive(fullH(st));
+                break;
+            }
             ++j;
         }
         return;

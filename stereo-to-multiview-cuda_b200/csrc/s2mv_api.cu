@@ -341,6 +341,8 @@ struct s2mv_ctx {
     int *line_ctr = nullptr;            // k_line2 work counters, one per pass
     CUtensorMap tmap_vol[2][2];         // tensor maps of the ping-pong volumes: [buffer A/B][row tile / column tile]
     CUtensorMap tmap_vv;                // buffer A, column tile of the fused vertical passes
+    int tmap_rows[2] = {1, 1}, tmap_rows_vv = 1;  // positions per tensor copy of those maps
+    int env_tmap_rows = 256;            // S2MV_TMAP_ROWS: wanted positions per tensor copy
     bool env_no_vv = false;             // S2MV_NO_VV: run the vertical passes as two launches
     bool tmap_ok = false;
     long long env_band_wait_spins = 20000000;  // S2MV_BAND_WAIT_SPINS: probes (1 us apart) before a halo wait gives up
@@ -440,6 +442,7 @@ extern "C" int s2mv_create(s2mv_ctx **out, int device)
     if (const char *e = getenv("S2MV_LINE_V1")) c->env_line_v1 = atoi(e) != 0;
     if (const char *e = getenv("S2MV_L2_CFG")) c->env_l2_cfg = atoi(e) == 1 ? 1 : 0;
     if (const char *e = getenv("S2MV_NO_VV")) c->env_no_vv = atoi(e) != 0;
+    if (const char *e = getenv("S2MV_TMAP_ROWS")) c->env_tmap_rows = std::max(1, atoi(e));
     if (const char *e = getenv("S2MV_LINE_BULK")) c->env_line_bulk = atoi(e) != 0;
     if (const char *e = getenv("S2MV_BAND_WAIT_SPINS")) c->env_band_wait_spins = atoll(e) > 0 ? atoll(e) : 1;
     c->device = device;
@@ -603,6 +606,14 @@ static EncodeTiledFn encode_tiled_fn()
     return fn;
 }
 
+// positions per tensor copy: the largest divisor of P not above `want`
+static int tmap_split_rows(int P, int want)
+{
+    for (int r = std::min(P, want); r > 1; --r)
+        if (P % r == 0) return r;
+    return 1;
+}
+
 static bool make_volume_tmaps(s2mv_ctx *c, size_t vol_rows)
 {
     const CostPlan &pl = c->plan;
@@ -614,8 +625,9 @@ static bool make_volume_tmaps(s2mv_ctx *c, size_t vol_rows)
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     for (int buf = 0; buf < 2; ++buf)
         for (int vert = 0; vert < 2; ++vert) {
-            const cuuint32_t P = (cuuint32_t)((vert ? pl.l2_S_v : pl.l2_S_h) + 2 * pl.l2_HP);
-            if (P > 256) return false;
+            const int Pfull = (vert ? pl.l2_S_v : pl.l2_S_h) + 2 * pl.l2_HP;
+            const cuuint32_t P = (cuuint32_t)tmap_split_rows(Pfull, c->env_tmap_rows);
+            c->tmap_rows[vert] = (int)P;
             const cuuint32_t box[4] = {128, vert ? 1u : P, vert ? P : 1u, 1};
             CUresult r = enc(&c->tmap_vol[buf][vert], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->vol[buf], gdim, gstr, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -623,7 +635,8 @@ static bool make_volume_tmaps(s2mv_ctx *c, size_t vol_rows)
             if (r != CUDA_SUCCESS) return false;
         }
     if (pl.vv) {
-        const cuuint32_t box[4] = {128, 1, (cuuint32_t)(pl.vv_S + 2 * pl.vv_HP), 1};
+        c->tmap_rows_vv = tmap_split_rows(pl.vv_S + 2 * pl.vv_HP, c->env_tmap_rows);
+        const cuuint32_t box[4] = {128, 1, (cuuint32_t)c->tmap_rows_vv, 1};
         CUresult r = enc(&c->tmap_vv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->vol[0], gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return false;
@@ -918,6 +931,7 @@ static int launch_pass(s2mv_ctx *c, LineArgs a, int pass, float4 *A, float4 *B, 
                              (nviews == 1 || view_stride4 == (size_t)(rr.vhi - rr.vlo) * W * pl.LPtot);
         L.use_tmap = c->tmap_ok && !ci && own_vol && !c->env_line_bulk;
         L.row_bias = rr.vlo;
+        L.tmap_rows = c->tmap_rows[vert ? 1 : 0];
         const CUtensorMap &tm = c->tmap_vol[src_buf][vert ? 1 : 0];
         CU(cudaMemsetAsync(L.counter, 0, sizeof(int), st));
         const int grid = std::min(c->sm_count, L.nclaims);
@@ -989,6 +1003,7 @@ static int launch_vv(s2mv_ctx *c, LineArgs a, float4 *Bout, size_t view_stride4,
     L.nz = nviews * a.nchunks;
     L.nclaims = L.nz * L.ncols;
     L.counter = c->line_ctr + 5;
+    L.tmap_rows = c->tmap_rows_vv;
     CU(cudaMemsetAsync(L.counter, 0, sizeof(int), st));
     const int grid = std::min(c->sm_count, L.nclaims);
     k_line_vv<kVVNA, kVVB><<<grid, (2 * kVVNA + kL2Producers) * 32, pl.vv_smem, st>>>(L, c->tmap_vv);

@@ -286,3 +286,21 @@ def test_host_registration_of_pageable_buffers(s2mv):
         with pytest.raises(s2mv.S2mvError):
             p.set_host_registration(3)
         p.set_host_registration(0)
+
+
+@pytest.mark.parametrize("env", [{}, {"S2MV_NO_VV": "1"}, {"S2MV_LINE_BULK": "1"}, {"S2MV_LINE_V1": "1"}, {"S2MV_L2_CFG": "1"}],
+                         ids=["default_fused_vertical", "separate_vertical_passes", "bulk_copies_no_tensor_map", "first_kernel_form",
+                              "tile_config_1"])
+def test_cost_volume_kernel_forms_agree_with_oracle(s2mv, oracle, env, monkeypatch):
+    # The cost volume has several code paths: the persistent pipelined kernels with the two vertical passes fused
+    # (default), the same with the vertical passes as two launches, with 512-byte bulk copies instead of tensor
+    # copies, the first kernel form (k_line; still what num_disp <= 64 runs), and the second tile geometry.  Each is
+    # held to the oracle on frames with several tiles per line, several lines per CTA, a ragged last tile in both
+    # directions and more rows than one vertical tile -- D = 128 (one chunk) and D = 200 (two chunks, padded).
+    from s2mv_b200_pkg import synth
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    with s2mv.Pipeline(0) as p:
+        for (H, W, D, zd, seed) in ((150, 700, 128, 64, 31), (70, 330, 200, 90, 32)):
+            got, want = run_both(p, oracle, synth.make_sbs(H, W, seed), W, D, zd)
+            assert_frame_equal(got, want)
