@@ -162,6 +162,9 @@ __device__ __forceinline__ void ci_fill_groups2(float4 *__restrict__ C4, const u
     const f32x2_t kMagic = pack2(-8388608.0f, -8388608.0f), kThird = pack2(0.33333333333f, 0.33333333333f),
                   kNegInv = pack2(-inv_ad, -inv_ad), kLog2e = pack2(1.4426950408889634f, 1.4426950408889634f),
                   kNegOne = pack2(-1.0f, -1.0f), kOne = pack2(1.0f, 1.0f);
+    // the census table as two halves: Hamming = popc(x) + 32 * bit31(x) (ref_hamdist32, d_alu.cu:7-15) -> the sign of the
+    // XOR picks the half, the popcount indexes it
+    const char *lutLo = reinterpret_cast<const char *>(sLutCen), *lutHi = lutLo + 128;
     for (int g = g_first; g < g_end; g += g_step) {
         const int p0 = 4 * g;
         const uint4 oP = *reinterpret_cast<const uint4 *>(sOwnP + p0);
@@ -174,6 +177,10 @@ __device__ __forceinline__ void ci_fill_groups2(float4 *__restrict__ C4, const u
         const uint32_t op[4] = {oP.x, oP.y, oP.z, oP.w}, oc[4] = {oC.x, oC.y, oC.z, oC.w};
         const uint32_t wp[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
         const uint32_t wc[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        // SURVEY Q4 columns (160m-1, 160m) inside this group?  r = first column of the group mod 160 (gx0 >= -HP)
+        const int gx0 = xb + p0;
+        const int r160 = (gx0 + 2 * kRefBlockW) % kRefBlockW;
+        const bool quirk = (r160 == 0 || r160 > kRefBlockW - 5) && gx0 < W;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             float r[4];
@@ -187,12 +194,12 @@ __device__ __forceinline__ void ci_fill_groups2(float4 *__restrict__ C4, const u
                     // left view (PLUS): other = R[x + (d - zd)] -> word i + j  (d_ci_ad.cu:133-144);
                     // right view: other = L[x - (d - zd)] -> word 4 + i - j
                     const int w = PLUS ? (i + j) : (4 + i - j);
-                    const uint32_t sad = __vsadu4(op[i], wp[w]);  // x byte is 0 in both
-                    fbits[u] = 0x4B000000u | sad;                 // (float)sad + 2^23, exact for sad < 2^23
+                    // (float)sad + 2^23 as bits: the sum of absolute byte differences accumulated onto 0x4B000000
+                    // (exact for sad < 2^23; the x byte is 0 in both words)
+                    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(fbits[u]) : "r"(op[i]), "r"(wp[w]), "r"(0x4B000000u));
                     const uint32_t x = oc[i] ^ wc[w];
-                    // ref_hamdist32 (d_alu.cu:7-15) = popc(x) + 32 * bit31(x), as a byte offset into the table
-                    const uint32_t off = ((uint32_t)__popc(x) << 2) + ((x >> 31) << 7);
-                    cen[u] = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(sLutCen) + off);
+                    const char *tb = (int)x < 0 ? lutHi : lutLo;
+                    cen[u] = *reinterpret_cast<const float *>(tb + 4 * __popc(x));
                 }
                 // ad_term (kernels_line.cuh) on the pair: the same five roundings per element, in the same order
                 f32x2_t t = add2(pack2(__uint_as_float(fbits[0]), __uint_as_float(fbits[1])), kMagic);
@@ -207,17 +214,19 @@ __device__ __forceinline__ void ci_fill_groups2(float4 *__restrict__ C4, const u
                 c = add2(c, pack2(cen[0], cen[1]));
                 unpack2(c, r[jj], r[jj + 1]);
             }
-            const int p = p0 + i, gx = xb + p;
-            const int tx = gx % kRefBlockW;
-            if ((tx == 0 || tx == kRefBlockW - 1) && gx >= 0 && gx < W) {
-                // the reference's 160-wide blocks read one slot outside their half at tx = 0 / 159
+            const int p = p0 + i;
+            if (quirk) {
+                const int gx = gx0 + i, tx = gx % kRefBlockW;
+                if ((tx == 0 || tx == kRefBlockW - 1) && gx >= 0 && gx < W) {
+                    // the reference's 160-wide blocks read one slot outside their half at tx = 0 / 159
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const CiOperands o = ref_ci_operands(view, gx, dbase + j < D ? dbase + j : 0, D, a.zd, W, a.pixL + row,
-                                                         a.pixR + row, a.cenL + row, a.cenR + row);
-                    const int sad = (int)__vsadu4(o.ad_own, o.ad_other);
-                    const int ham = ref_hamdist32(o.cen_own, o.cen_other);
-                    r[j] = __fadd_rn(ad_term(sad, inv_ad), sLutCen[ham]);
+                    for (int j = 0; j < 4; ++j) {
+                        const CiOperands o = ref_ci_operands(view, gx, dbase + j < D ? dbase + j : 0, D, a.zd, W, a.pixL + row,
+                                                             a.pixR + row, a.cenL + row, a.cenR + row);
+                        const int sad = (int)__vsadu4(o.ad_own, o.ad_other);
+                        const int ham = ref_hamdist32(o.cen_own, o.cen_other);
+                        r[j] = __fadd_rn(ad_term(sad, inv_ad), sLutCen[ham]);
+                    }
                 }
             }
             if (!FULL_D) {
