@@ -36,7 +36,7 @@ namespace s2mv {
 
 constexpr int kL2MaxConsumers = 16;
 constexpr int kL2DescRing = 8;
-constexpr int kL2MaxBlocks = 16;       // output blocks per tile (S / B)
+constexpr int kL2MaxBlocks = 32;       // output blocks per tile (S / B), at most
 constexpr uint32_t kL2PosBytes = 512;  // one tile position: 32 lanes x float4
 
 struct Line2Args {
@@ -130,13 +130,13 @@ __host__ __device__ inline size_t line2_align16(size_t b) { return (b + 15) & ~(
 __host__ __device__ inline int line2_frame(int B, int HP) { return (B + 2 * HP + 1) & ~1; }  // mask positions per block
 __host__ __device__ inline size_t line2_smem_bytes(int S, int HP, int B, bool ci, int kL2Stages)
 {
-    const size_t P = (size_t)S + 2 * HP;
+    const size_t P = (size_t)S + 2 * HP, NBT = (size_t)(S + B - 1) / B;
     size_t b = 128;                                                                     // alignment slack of the tile base
     b += kL2Stages * P * kL2PosBytes;                                                   // tiles
     b += 128;                                                                           // mbarriers
     b += line2_align16(kL2DescRing * sizeof(Line2Desc));                                // descriptors
-    b += line2_align16((size_t)kL2DescRing * kL2MaxBlocks * line2_frame(B, HP) * 2);    // window masks (u16)
-    b += line2_align16((size_t)kL2DescRing * kL2MaxBlocks * 4);                         // walk bounds per block
+    b += line2_align16((size_t)kL2DescRing * NBT * line2_frame(B, HP) * 2);             // window masks (u16)
+    b += line2_align16((size_t)kL2DescRing * NBT * 4);                                  // walk bounds per block
     b += line2_align16(kL2Stages * (ci ? (4 * P + 256) * 4 : 0)) + 80 * 4;              // operand words, census table
     b += kL2DescRing * 4;                                                               // claimed runs (producer warps)
     return b;
@@ -246,20 +246,22 @@ __device__ __forceinline__ void ci_fill_groups2(float4 *__restrict__ C4, const u
 // bounds (first position | end position << 16; 0 = nothing to add).
 constexpr int kL2Producers = 4;
 
-// This lane's output block of a tile of nb blocks (one block per group of 8 lanes, 16 per tile) or -1
+// This lane's output block of a tile of nb blocks (one block per group of LPB lanes: 128 / LPB blocks per tile
+// over the four producer warps) or -1
+template <int LPB>
 __device__ __forceinline__ int mask_lane_block(int pw, int lane, int nb)
 {
-    const int i = pw * 4 + (lane >> 3);
+    const int i = pw * (32 / LPB) + lane / LPB;
     return i < nb ? i : -1;
 }
 
 // Masks and walk bounds of one block from its B arm words (0 = output outside the line): this lane writes the
-// frame positions of its slice (8 lanes share a block), the first lane of the block the bounds.
-template <int B, bool VERT>
+// frame positions of its slice (LPB lanes share a block), the first lane of the block the bounds.
+template <int B, bool VERT, int LPB>
 __device__ __forceinline__ void masks_from_arms(uint16_t *__restrict__ mrow, uint32_t *__restrict__ bound, const uint32_t ar[B],
                                                 int HP, int lane)
 {
-    const int FR = line2_frame(B, HP), PL = (FR + 7) / 8, slice = lane & 7;
+    const int FR = line2_frame(B, HP), PL = (FR + LPB - 1) / LPB, slice = lane % LPB;
     uint32_t s_rel[B], len[B];
     int first = 0x7fffffff, end = 0;
 #pragma unroll
@@ -362,11 +364,12 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
     sp += 128;
     Line2Desc *desc = reinterpret_cast<Line2Desc *>(sp);
     sp += line2_align16(kL2DescRing * sizeof(Line2Desc));
-    const int FR = line2_frame(B, HP);
+    const int FR = line2_frame(B, HP), NBT = (S + B - 1) / B;
+    constexpr int LPB = B <= 4 ? 4 : 8;  // producer lanes per block: up to 32 (short) or 16 blocks per tile
     uint16_t *sMask = reinterpret_cast<uint16_t *>(sp);  // [ring][block][frame position]
-    sp += line2_align16((size_t)kL2DescRing * kL2MaxBlocks * FR * 2);
+    sp += line2_align16((size_t)kL2DescRing * NBT * FR * 2);
     uint32_t *sBounds = reinterpret_cast<uint32_t *>(sp);  // [ring][block]
-    sp += line2_align16((size_t)kL2DescRing * kL2MaxBlocks * 4);
+    sp += line2_align16((size_t)kL2DescRing * NBT * 4);
     uint32_t *sOps = reinterpret_cast<uint32_t *>(sp);  // CI: per stage ownP[P] ownC[P] othP[P+128] othC[P+128]
     const int OPS = CI ? 4 * P + 256 : 0;
     float *sLutCen = reinterpret_cast<float *>(sp + line2_align16((size_t)NS * OPS * 4));
@@ -498,7 +501,7 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
             // Window masks, one tile behind: the arm words of THIS tile are requested now and turned into masks in
             // the next trip, so their load latency never sits between two tiles.
             uint32_t nxt[B];
-            const int my_b = valid ? mask_lane_block(pw, lane, S / B) : -1;
+            const int my_b = valid ? mask_lane_block<LPB>(pw, lane, NBT) : -1;
 #pragma unroll
             for (int i = 0; i < B; ++i) {
                 const int o = my_b * B + i;
@@ -507,8 +510,8 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
             }
             if (pend_bar) {
                 if (pend_b >= 0)
-                    masks_from_arms<B, VERT>(sMask + ((size_t)pend_ring * kL2MaxBlocks + pend_b) * FR, sBounds + pend_ring * kL2MaxBlocks + pend_b,
-                                             cur, HP, lane);
+                    masks_from_arms<B, VERT, LPB>(sMask + ((size_t)pend_ring * NBT + pend_b) * FR, sBounds + pend_ring * NBT + pend_b, cur, HP,
+                                                  lane);
                 mbar_arrive(pend_bar);  // releases this lane's masks (leader lane 0: and the descriptor)
             }
 #pragma unroll
@@ -589,7 +592,7 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
         for (int b = warp; b < nblocks; b += NW) {
             const int o0 = b * B, nvalid = min(B, Sact - o0);
             float4 acc[B];
-            sum_block_masked<B>(tq, smem_u32(sMask + ((size_t)ring * kL2MaxBlocks + b) * FR), sBounds[ring * kL2MaxBlocks + b], o0, acc);
+            sum_block_masked<B>(tq, smem_u32(sMask + ((size_t)ring * NBT + b) * FR), sBounds[ring * NBT + b], o0, acc);
             if (MODE != LM_H_WTA) {
                 char *dstp = reinterpret_cast<char *>(a.out[vslot] + line_base4) + (long long)(t0 + o0) * ostride;
 #pragma unroll
@@ -762,7 +765,7 @@ k_line_vv(const __grid_constant__ LineVVArgs L, const __grid_constant__ CUtensor
             int my_slot = -1;
             {
                 const int nb = valid ? NBS + (j == 0 ? NBH : 0) : 0;
-                const int i = mask_lane_block(pw, lane, nb);
+                const int i = mask_lane_block<8>(pw, lane, nb);
                 const int g = (j == 0 ? 0 : NBH + j * NBS) + i;
                 if (i >= 0) my_slot = (colbase + g) % kVVMaskRing;
 #pragma unroll
@@ -773,7 +776,7 @@ k_line_vv(const __grid_constant__ LineVVArgs L, const __grid_constant__ CUtensor
                 }
             }
             if (pend_bar) {
-                if (pend_slot >= 0) masks_from_arms<B, true>(sMask + (size_t)pend_slot * FR, sBounds + pend_slot, cur, HP, lane);
+                if (pend_slot >= 0) masks_from_arms<B, true, 8>(sMask + (size_t)pend_slot * FR, sBounds + pend_slot, cur, HP, lane);
                 mbar_arrive(pend_bar);
             }
 #pragma unroll

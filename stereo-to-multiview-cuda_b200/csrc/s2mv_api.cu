@@ -139,9 +139,10 @@ struct CostPlan {
 // k_line2 configurations (consumer warps NW, outputs per block B, ring stages NS, outputs per tile ~ NW * B):
 //   cfg 0: loaded-tile passes 16 x 6, 3 stages of ~96 outputs;  pass 1 (tiles are computed) 12 x 8, 3 stages
 //   cfg 1: every pass 16 x 4, 4 stages of ~64 outputs (one more tile in flight, shorter blocks)
+//   cfg 2: as cfg 0, but pass 1 sums blocks of 4 outputs, two per warp (96 outputs per tile)
 constexpr int kVVNA = 8, kVVB = 6;   // k_line_vv: 8 + 8 consumer warps, 6 rows per block, 48 rows per tile
 struct L2Cfg { int NW, B, NS; };
-static const L2Cfg kL2Cfg[2][2] = {{{16, 6, 3}, {12, 8, 3}}, {{16, 4, 4}, {16, 4, 4}}};  // [cfg][0 loaded, 1 computed]
+static const L2Cfg kL2Cfg[3][2] = {{{16, 6, 3}, {12, 8, 3}}, {{16, 4, 4}, {16, 4, 4}}, {{16, 6, 3}, {12, 4, 3}}};  // [cfg][0 loaded, 1 computed]
 
 // outputs per tile along a line of `len` outputs: close to NW * B, a multiple of the block size, the line cut evenly
 static int line2_segment(int len, int B, int NW)
@@ -238,7 +239,7 @@ static int make_plan(CostPlan &pl, int H, int W, int D, int zd, int usd, int l2_
         pl.l2_cfg = l2_cfg;
         const L2Cfg &ld = kL2Cfg[l2_cfg][0], &ci = kL2Cfg[l2_cfg][1];
         pl.l2_HP = (usd + 1) & ~1;
-        pl.l2_S_ci = line2_segment(W, ci.B, ci.NW);
+        pl.l2_S_ci = l2_cfg == 2 ? line2_segment(W, 8, 12) : line2_segment(W, ci.B, ci.NW);
         pl.l2_S_h = line2_segment(W, ld.B, ld.NW);
         pl.l2_S_v = line2_segment(H, ld.B, ld.NW);
         pl.l2_smem_ci = line2_smem_bytes(pl.l2_S_ci, pl.l2_HP, ci.B, true, ci.NS);
@@ -440,7 +441,7 @@ extern "C" int s2mv_create(s2mv_ctx **out, int device)
     if (const char *e = getenv("S2MV_IRV_DENSE_MIN")) c->env_irv_dense_min = atoi(e) < 0 ? 0 : atoi(e);
     if (const char *e = getenv("S2MV_BILATERAL_SCALAR")) c->env_bilateral_scalar = atoi(e) != 0;
     if (const char *e = getenv("S2MV_LINE_V1")) c->env_line_v1 = atoi(e) != 0;
-    if (const char *e = getenv("S2MV_L2_CFG")) c->env_l2_cfg = atoi(e) == 1 ? 1 : 0;
+    if (const char *e = getenv("S2MV_L2_CFG")) c->env_l2_cfg = std::min(2, std::max(0, atoi(e)));
     if (const char *e = getenv("S2MV_NO_VV")) c->env_no_vv = atoi(e) != 0;
     if (const char *e = getenv("S2MV_TMAP_ROWS")) c->env_tmap_rows = std::max(1, atoi(e));
     if (const char *e = getenv("S2MV_LINE_BULK")) c->env_line_bulk = atoi(e) != 0;
@@ -524,6 +525,7 @@ static int set_kernel_attrs()
     TRY((set_smem(k_line_vv<kVVNA, kVVB>, big)));
     TRY((set_smem(k_line2<LM_CI_H, 12, 8, 3>, big)));
     TRY((set_smem(k_line2<LM_CI_H, 16, 4, 4>, big)));
+    TRY((set_smem(k_line2<LM_CI_H, 12, 4, 3>, big)));
     TRY((set_line2_attrs<16, 6, 3>()));
     TRY((set_line2_attrs<16, 4, 4>()));
     TRY(set_smem(k_bilateral, 160 * 1024));
@@ -938,8 +940,9 @@ static int launch_pass(s2mv_ctx *c, LineArgs a, int pass, float4 *A, float4 *B, 
         const int mode = ci ? LM_CI_H : (vert ? LM_V : ((pass == 4 && to_wta) ? LM_H_WTA : LM_H));
         const size_t smem = ci ? pl.l2_smem_ci : (vert ? pl.l2_smem_v : pl.l2_smem_h);
 #define S2MV_L2_LAUNCH(MODE, NW, B, NS) k_line2<MODE, NW, B, NS><<<grid, (NW + kL2Producers) * 32, smem, st>>>(L, tm)
-        if (pl.l2_cfg == 0) {
-            if (mode == LM_CI_H) S2MV_L2_LAUNCH(LM_CI_H, 12, 8, 3);
+        if (pl.l2_cfg != 1) {
+            if (mode == LM_CI_H && pl.l2_cfg == 2) S2MV_L2_LAUNCH(LM_CI_H, 12, 4, 3);
+            else if (mode == LM_CI_H) S2MV_L2_LAUNCH(LM_CI_H, 12, 8, 3);
             else if (mode == LM_V) S2MV_L2_LAUNCH(LM_V, 16, 6, 3);
             else if (mode == LM_H_WTA) S2MV_L2_LAUNCH(LM_H_WTA, 16, 6, 3);
             else S2MV_L2_LAUNCH(LM_H, 16, 6, 3);
