@@ -63,6 +63,10 @@ struct IrvArgs {
     // dense path (k_irv_hseg + k_irv_vote_dense): per-pixel histograms of the horizontal arm span
     uint8_t *hseg[2];    // [pixel][nbp] counts, nbp = nbins rounded up to a multiple of 128; null: sparse path only
     int nbp;
+    // incremental iterations (dense path): stamp[pixel] = 1 + the iteration whose vote changed the pixel (0: never);
+    // hchg[pixel] = the pixel's horizontal span holds a pixel changed by the previous iteration
+    uint8_t *stamp[2];
+    uint8_t *hchg[2];
     int dense_min;       // list length from which an iteration takes the dense path
 };
 constexpr int kNoVote = -0x7fffffff;
@@ -218,11 +222,17 @@ constexpr int kHsegThreads = 128;
 #define S2MV_IRV_BATCH 4
 #endif
 
+// From the second iteration on only the pixels whose span holds a pixel the previous iteration changed are
+// rebuilt (the vote of iteration t reads the state after iteration t-1; a span without a change has the histogram
+// it had): the kernel first looks at the change stamps of the tile and its arm reach and, in the common case of a
+// late iteration, leaves the tile alone.  hchg records per pixel whether its span changed, for k_irv_vote_dense.
 template <int NW>  // 128-bin words per pixel: nbp = 128 * NW
 __global__ void __launch_bounds__(kHsegThreads)
 k_irv_hseg(const IrvArgs a)
 {
     extern __shared__ __align__(16) uint8_t hs[];  // [kHsegThreads][nbp + 4]: the pad staggers the banks
+    __shared__ uint8_t chg[kHsegThreads + 2 * 64];  // "changed by the previous iteration", tile + arm reach (usd <= 64)
+    __shared__ uint8_t need[kHsegThreads];
     const int v = blockIdx.y;
     if (irv_settled(a, v) || *a.count[v] < a.dense_min) return;
     constexpr int nbp = 128 * NW, pitch = nbp + 4;
@@ -231,26 +241,50 @@ k_irv_hseg(const IrvArgs a)
     const float *__restrict__ disp = a.disp[v];
     const uint8_t *__restrict__ outl = a.outliers[v];
     const uint32_t *__restrict__ arms = a.arms[v];
+    const uint8_t *__restrict__ stamp = a.stamp[v];
     uint8_t *__restrict__ hseg = a.hseg[v];
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const bool incremental = a.it > 0 && stamp != nullptr;
     uint32_t *hw = reinterpret_cast<uint32_t *>(hs);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int gy = tile / tiles_x, bx = (tile - gy * tiles_x) * kHsegThreads;
+        const int gx = bx + t;
+        const size_t row = (size_t)gy * W;
+        int mine = 1;  // this pixel's histogram has to be (re)built
+        if (incremental) {
+            int any = 0;
+            for (int i = t; i < kHsegThreads + 2 * a.usd; i += kHsegThreads) {
+                const int x = bx - a.usd + i;
+                const uint8_t c = (x >= 0 && x < W && stamp[row + x] == (uint8_t)a.it) ? 1 : 0;
+                chg[i] = c;
+                any |= c;
+            }
+            if (!__syncthreads_or(any)) {  // nothing in reach changed: histograms and flags of the tile stand
+                if (gx < W) a.hchg[v][row + gx] = 0;
+                continue;
+            }
+            mine = 0;
+            if (gx < W) {
+                const uint32_t ar = arms[row + gx];
+                const int cl = arm_left(ar), cr = arm_right(ar);
+                for (int k = -cl; k <= cr; ++k) mine |= chg[t + a.usd + k];
+                a.hchg[v][row + gx] = (uint8_t)mine;
+            }
+        }
+        need[t] = (uint8_t)(mine && gx < W);
         {
             uint4 *z = reinterpret_cast<uint4 *>(hs);  // kHsegThreads * pitch bytes is a multiple of 16
             for (int i = t; i < kHsegThreads * pitch / 16; i += kHsegThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
         }
         __syncthreads();
-        const int gx = bx + t;
-        if (gx < W) {
-            const size_t row = (size_t)gy * W;
+        if (gx < W && mine) {
             const uint32_t ar = arms[row + gx];
             const int cl = arm_left(ar), span = cl + arm_right(ar) + 1;  // inclusive [-L, R]
             const float *__restrict__ dp = disp + row + (gx - cl);
             const uint8_t *__restrict__ op = outl + row + (gx - cl);
-            uint8_t *mine = hs + t * pitch;
+            uint8_t *h = hs + t * pitch;
             for (int k = 0; k < span; ++k)
-                if (op[k] == 0) mine[clampi((int)dp[k] + a.zd, 0, a.nbins - 1)] += 1;
+                if (op[k] == 0) h[clampi((int)dp[k] + a.zd, 0, a.nbins - 1)] += 1;
         }
         __syncthreads();
         // out: one pixel's nbp bytes per warp step, 128 bytes per store instruction, pointers walked by increments
@@ -259,6 +293,7 @@ k_irv_hseg(const IrvArgs a)
         uint32_t *__restrict__ d = reinterpret_cast<uint32_t *>(hseg + ((size_t)gy * W + bx) * nbp) + (size_t)warp * wpp + lane;
         const uint32_t *sp = hw + warp * wps + lane;
         for (int i = warp; i < npix; i += kHsegThreads / 32, d += (kHsegThreads / 32) * wpp, sp += (kHsegThreads / 32) * wps) {
+            if (!need[i]) continue;
 #pragma unroll
             for (int w = 0; w < NW; ++w) d[32 * w] = sp[32 * w];
         }
@@ -295,6 +330,16 @@ k_irv_vote_dense(const IrvArgs a)
         const int gy = pix / W, gx = pix - gy * W;
         const uint32_t ac = arms[pix];
         const int cu = min(arm_up(ac), a.usd), nrows = cu + arm_down(ac) + 1;  // rows [-cu, +cd] inclusive
+        if (a.it > 0 && a.stamp[v] != nullptr) {
+            // Still on the list = its last vote was rejected.  If no pixel of its support changed since (no support
+            // row's span holds a pixel the previous iteration changed), the same vote would be rejected again.
+            int hit = 0;
+            for (int r = lane; r < nrows; r += 32) hit |= a.hchg[v][(size_t)(gy - cu + r) * W + gx];
+            if (!__any_sync(0xffffffffu, hit)) {
+                if (lane == 0) a.vote[v][e] = kNoVote;
+                continue;
+            }
+        }
         uint32_t lo[NW], hi[NW];  // 16-bit fields: bins (0, 2) and (1, 3) of each packed word
 #pragma unroll
         for (int w = 0; w < NW; ++w) lo[w] = hi[w] = 0u;
@@ -351,6 +396,7 @@ k_irv_apply(const IrvArgs a)
             if (vote != kNoVote) {
                 a.outliers[v][pix] = 0;
                 a.disp[v][pix] = (float)vote;
+                if (a.stamp[v]) a.stamp[v][pix] = (uint8_t)(a.it + 1);
                 pix = -1;
                 ++taken;
             }

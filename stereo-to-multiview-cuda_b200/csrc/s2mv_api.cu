@@ -314,6 +314,7 @@ struct s2mv_ctx {
     uint8_t *outl[2] = {}, *disoccl[2] = {};
     int *irv_list[2] = {}, *irv_list2[2] = {}, *irv_vote[2] = {}, *irv_count = nullptr;
     uint8_t *irv_hseg[2] = {};  // dense region-voting histograms, [pixel][nbp]; null when not allocated
+    uint8_t *irv_stamp[2] = {}, *irv_hchg[2] = {};  // incremental dense voting: change stamps, "span changed" flags
     int irv_nbp = 0;
     float *bil_spatial = nullptr, *bil_colour = nullptr, *gauss_kernel = nullptr;
     std::vector<float> h_gauss_kernel;  // host copy of gauss_kernel (for its fp32 sum)
@@ -708,6 +709,8 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
         TRY(dev_alloc_t(c, &c->irv_list[v], n + 16));
         TRY(dev_alloc_t(c, &c->irv_list2[v], n + 16));
         TRY(dev_alloc_t(c, &c->irv_vote[v], n));
+        TRY(dev_alloc_t(c, &c->irv_stamp[v], n));
+        TRY(dev_alloc_t(c, &c->irv_hchg[v], n));
         TRY(dev_alloc_t(c, &c->occl[v], n));
         TRY(dev_alloc_t(c, &c->occlB[v], n));
         TRY(dev_alloc_t(c, &c->mask[v], n));
@@ -1146,7 +1149,13 @@ static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2],
     // the bin count (bytes per pixel histogram), the sparse one's does not
     a.dense_min = (int)(n / 32) * (c->irv_nbp > 128 ? c->irv_nbp / 128 : 1) + 1;
     if (c->env_irv_dense_min >= 0) a.dense_min = c->env_irv_dense_min;  // test hook (read at create): 0 = always dense, huge = never
-    for (int v = 0; v < nviews; ++v) a.hseg[v] = dense_ok ? c->irv_hseg[v] : nullptr;
+    for (int v = 0; v < nviews; ++v) {
+        a.hseg[v] = dense_ok ? c->irv_hseg[v] : nullptr;
+        a.stamp[v] = dense_ok ? c->irv_stamp[v] : nullptr;
+        a.hchg[v] = dense_ok ? c->irv_hchg[v] : nullptr;
+        if (dense_ok && iterations > 1 && iterations < 255) CU(cudaMemsetAsync(c->irv_stamp[v], 0, n, st));
+    }
+    if (iterations >= 255) for (int v = 0; v < nviews; ++v) a.stamp[v] = nullptr;
     for (int it = 0; it < iterations; ++it) {
         a.it = it;
         if (dense_ok) {
