@@ -298,6 +298,12 @@ int s2mv_dibr_dbm(s2mv_ctx *ctx, uint8_t *img_out, const uint8_t *img_in_l, cons
                   const float *disp_l, const float *disp_r, const float *mask_l, const float *mask_r,
                   float shift, int blur_radius, float blur_sigma,
                   int num_rows, int num_cols, int elem_sz);
+/* d_dibr_fwarp.cu:97-197 (dibr_dfm): forward-warp alternative to dibr_dbm.  Neither reference driver calls it and its
+ * scatter races when several sources land on one destination (no ordering); here the lowest source column wins.
+ * PARITY UNPINNED on colliding destinations; identical to the reference everywhere else (tests/test_fwarp.py). */
+int s2mv_dibr_dfm(s2mv_ctx *ctx, uint8_t *img_out, const uint8_t *img_in_l, const uint8_t *img_in_r,
+                  const float *disp_l, const float *disp_r, float shift,
+                  int num_rows, int num_cols, int elem_sz);
 /* d_mux_multiview.cu:155-222; kernel_variant 0 = choose as the reference does
  * (kernel 2 when num_rows_out % num_views == 0, else kernel 1) */
 int s2mv_mux_multiview(s2mv_ctx *ctx, uint8_t **views, uint8_t *out, int num_views, float angle,

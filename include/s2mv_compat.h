@@ -56,6 +56,9 @@ void filter_gaussian_1(float *img, int radius, float sigma_spatial, int num_rows
 void dibr_dbm(unsigned char *img_out, unsigned char *img_in_l, unsigned char *img_in_r, float *disp_l,
               float *disp_r, unsigned char *occl_l, unsigned char *occl_r, float *mask_l, float *mask_r,
               float shift, int num_rows, int num_cols, int elem_sz);
+/* d_dibr_fwarp.h:18-21  _Z8dibr_dfmPhS_S_PfS0_fiii  (never called by the reference's drivers; s2mv.h: s2mv_dibr_dfm) */
+void dibr_dfm(unsigned char *img_out, unsigned char *img_in_l, unsigned char *img_in_r, float *disp_l, float *disp_r,
+              float shift, int num_rows, int num_cols, int elem_sz);
 /* d_mux_multiview.h  _Z13mux_multiviewPPhS_ifiiiii */
 void mux_multiview(unsigned char **views, unsigned char *out_data, int num_views, float angle, int in_rows,
                    int in_cols, int out_rows, int out_cols, int elem_sz);

@@ -247,6 +247,25 @@ def dbm(img_l, img_r, disp_l, disp_r, mask_l, mask_r, shift, gauss_radius=10, ga
     return out
 
 
+def fwarp(img, disp, shift, want_hits=False):
+    """dibr_forward_warp_kernel with the lowest-source-column-wins rule; hits = sources per destination."""
+    H, W, es = img.shape
+    out = np.zeros_like(img)
+    hits = np.zeros((H, W), np.int32)
+    lib().orc_fwarp(_p(out), _p(np.ascontiguousarray(img)), _p(np.ascontiguousarray(disp, np.float32)), _f(shift),
+                    _p(hits), H, W, es)
+    return (out, hits) if want_hits else out
+
+
+def dibr_dfm(img_l, img_r, disp_l, disp_r, shift):
+    H, W, es = img_l.shape
+    out = np.zeros_like(img_l)
+    lib().orc_dibr_dfm(_p(out), _p(np.ascontiguousarray(img_l)), _p(np.ascontiguousarray(img_r)),
+                       _p(np.ascontiguousarray(disp_l, np.float32)), _p(np.ascontiguousarray(disp_r, np.float32)),
+                       _f(shift), H, W, es)
+    return out
+
+
 def mux_multiview(views, angle, Ho, Wo, kernel_variant=2):
     views = [np.ascontiguousarray(v) for v in views]
     V = len(views)

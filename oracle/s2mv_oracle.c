@@ -718,6 +718,44 @@ void orc_merge_ab(uint8_t *img_b, const uint8_t *img_a, const float *mask_a,
     }
 }
 
+/* dibr_forward_warp_kernel (d_dibr_fwarp.cu:9-25).  The reference's scatter has no ordering between sources
+ * that land on one destination; this statement fixes it: the row is scanned right to left, so the
+ * LOWEST source column wins (the outcome the reference's kernel is observed to produce on a B200 for ~98 % of the
+ * colliding destinations).  `hits` (optional) receives the number of sources per destination, so that a test
+ * can tell the destinations on which the reference itself is well defined (hits <= 1).  PARITY UNPINNED on the
+ * others. */
+void orc_fwarp(uint8_t *out, const uint8_t *in, const float *disp, float shift, int *hits,
+               int num_rows, int num_cols, int elem_sz)
+{
+    memset(out, 0, (size_t)num_rows * num_cols * elem_sz);
+    if (hits) memset(hits, 0, (size_t)num_rows * num_cols * sizeof(int));
+    for (int ty = 0; ty < num_rows; ++ty)
+        for (int tx = num_cols - 1; tx >= 0; --tx) {
+            size_t i = (size_t)ty * num_cols + tx;
+            int sd = (int)(disp[i] * shift);
+            int sx = tx + sd;
+            sx = sx < 0 ? 0 : (sx > num_cols - 1 ? num_cols - 1 : sx);
+            size_t o = (size_t)ty * num_cols + sx;
+            for (int c = 0; c < 3; ++c) out[o * elem_sz + c] = in[i * elem_sz + c];
+            if (hits) hits[o] += 1;
+        }
+}
+
+/* d_dibr_dfm (d_dibr_fwarp.cu:27-95): both forward warps, then mux_merge_AB(out_l, out_r, mask) with the mask of a
+ * zeroed occlusion map (0 everywhere: :55-66), i.e. the left warp survives. */
+void orc_dibr_dfm(uint8_t *out, const uint8_t *img_l, const uint8_t *img_r, const float *disp_l, const float *disp_r,
+                  float shift, int num_rows, int num_cols, int elem_sz)
+{
+    size_t plane = (size_t)num_rows * num_cols;
+    uint8_t *out_r = (uint8_t *)malloc(plane * elem_sz);
+    float *mask = (float *)calloc(plane, sizeof(float));
+    orc_fwarp(out, img_l, disp_l, shift, NULL, num_rows, num_cols, elem_sz);
+    orc_fwarp(out_r, img_r, disp_r, (float)(1.0 - shift), NULL, num_rows, num_cols, elem_sz);
+    orc_merge_ab(out, out_r, mask, num_rows, num_cols, elem_sz);
+    free(out_r);
+    free(mask);
+}
+
 void orc_dbm(uint8_t *out, const uint8_t *img_l, const uint8_t *img_r,
              const float *disp_l, const float *disp_r, const float *mask_l, const float *mask_r,
              float shift, int gauss_radius, float gauss_sigma,

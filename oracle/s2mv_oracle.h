@@ -97,6 +97,10 @@ void orc_gaussian_dilate(float *img, int radius, float sigma, int num_rows, int 
 void orc_bwarp(uint8_t *out, const uint8_t *in, const float *mask, const float *disp,
                float shift, int num_rows, int num_cols, int elem_sz);
 /* d_mux_common.cu:23-46 */
+void orc_fwarp(uint8_t *out, const uint8_t *in, const float *disp, float shift, int *hits,
+               int num_rows, int num_cols, int elem_sz);
+void orc_dibr_dfm(uint8_t *out, const uint8_t *img_l, const uint8_t *img_r, const float *disp_l, const float *disp_r,
+                  float shift, int num_rows, int num_cols, int elem_sz);
 void orc_merge_ab(uint8_t *img_b, const uint8_t *img_a, const float *mask_a,
                   int num_rows, int num_cols, int elem_sz);
 /* d_dibr_bwarp.cu:24-70 (radius 10 sigma 15) / :75-183 (radius 7 sigma 10) */

@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "s2mv_read_taps", "s2mv_ci_adcensus", "s2mv_gray", "s2mv_census", "s2mv_ci_ad", "s2mv_ci_census",
     "s2mv_ca_cross", "s2mv_dc_wta", "s2mv_dr_dcc", "s2mv_dr_irv", "s2mv_filter_bilateral_1",
     "s2mv_dibr_occl", "s2mv_filter_bleed_1", "s2mv_dibr_occl_to_mask", "s2mv_filter_gaussian_1",
-    "s2mv_dibr_dbm", "s2mv_mux_multiview",
+    "s2mv_dibr_dbm", "s2mv_dibr_dfm", "s2mv_mux_multiview",
     "s2mv_stream_open", "s2mv_stream_input_buffer", "s2mv_stream_submit", "s2mv_stream_collect",
     "s2mv_stream_pending", "s2mv_stream_close", "s2mv_set_chunk_sequential", "s2mv_is_chunk_sequential",
     "s2mv_configure_band", "s2mv_band_info", "s2mv_band_prepare", "s2mv_band_pass", "s2mv_band_halo",
@@ -40,7 +40,7 @@ COMPAT_SYMBOLS = [
     "_Z6dr_irvPfPhPS0_ifiiiiii", "_Z18filter_bilateral_1Pfiffiii", "_Z9dibr_occlPhS_PfS0_ii",
     "_Z14filter_bleed_1Phiii", "_Z17dibr_occl_to_maskPfS_PhS0_ii", "_Z17filter_gaussian_1Pfifii",
     "_Z8dibr_dbmPhS_S_PfS0_S_S_S0_S0_fiii", "_Z13mux_multiviewPPhS_ifiiiii", "_Z7dc_hsloPPfS_PhS1_fffiiiii",
-    "_Z14adcensus_stm_2PhPfS0_S_iiiiiiiifiiiiffffiiif",
+    "_Z14adcensus_stm_2PhPfS0_S_iiiiiiiifiiiiffffiiif", "_Z8dibr_dfmPhS_S_PfS0_fiii",
 ]
 
 
@@ -471,6 +471,15 @@ class Pipeline:
         args = [np.ascontiguousarray(a, np.float32) for a in (disp_l, disp_r, mask_l, mask_r)]
         _check(self._L.s2mv_dibr_dbm(self._ctx, _p(out), _p(img_l), _p(img_r), *[_p(a) for a in args], _f(shift),
                                      blur_radius, _f(blur_sigma), H, W, es))
+        return out
+
+    def dibr_dfm(self, img_l, img_r, disp_l, disp_r, shift):
+        """Forward-warp view synthesis (d_dibr_fwarp.cu:97-197); colliding sources: lowest source column wins."""
+        H, W, es = img_l.shape
+        out = np.zeros((H, W, es), np.uint8)
+        args = [np.ascontiguousarray(a, np.float32) for a in (disp_l, disp_r)]
+        _check(self._L.s2mv_dibr_dfm(self._ctx, _p(out), _p(np.ascontiguousarray(img_l)), _p(np.ascontiguousarray(img_r)),
+                                     *[_p(a) for a in args], _f(shift), H, W, es))
         return out
 
     def mux_multiview(self, views, angle, num_rows_out, num_cols_out, kernel_variant=0):

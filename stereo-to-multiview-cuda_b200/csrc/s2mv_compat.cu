@@ -156,6 +156,12 @@ void dibr_dbm(unsigned char *img_out, unsigned char *img_in_l, unsigned char *im
                         num_rows, num_cols, elem_sz), "dibr_dbm");
 }
 
+void dibr_dfm(unsigned char *img_out, unsigned char *img_in_l, unsigned char *img_in_r, float *disp_l, float *disp_r,
+              float shift, int num_rows, int num_cols, int elem_sz)
+{
+    check(s2mv_dibr_dfm(nullptr, img_out, img_in_l, img_in_r, disp_l, disp_r, shift, num_rows, num_cols, elem_sz), "dibr_dfm");
+}
+
 void mux_multiview(unsigned char **views, unsigned char *out_data, int num_views, float angle, int in_rows,
                    int in_cols, int out_rows, int out_cols, int elem_sz)
 {

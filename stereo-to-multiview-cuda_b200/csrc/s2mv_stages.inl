@@ -459,6 +459,48 @@ extern "C" int s2mv_dibr_dbm(s2mv_ctx *ctx, uint8_t *img_out, const uint8_t *img
     return S2MV_OK;
 }
 
+// d_dibr_dfm (d_dibr_fwarp.cu:27-95): forward-warp the left image by disp_l * shift and the right one by
+// disp_r * (1 - shift), then mux_merge_AB(out_l, out_r, mask) with the mask the reference builds from an
+// all-zero occlusion map -- i.e. 0 everywhere, so the merged image is the left warp (reproduced as written).
+// Colliding sources: the lowest source column wins (kernels_dibr.cuh; the reference races).
+extern "C" int s2mv_dibr_dfm(s2mv_ctx *ctx, uint8_t *img_out, const uint8_t *img_in_l, const uint8_t *img_in_r,
+                             const float *disp_l, const float *disp_r, float shift, int H, int W, int elem_sz)
+{
+    if (!img_out || !img_in_l || !img_in_r || !disp_l || !disp_r) return fail(S2MV_ERR_BAD_PARAM, "null argument");
+    if (elem_sz != 3) return fail(S2MV_ERR_BAD_PARAM, "elem_sz must be 3");
+    s2mv_ctx *c;
+    TRY(acquire(ctx, H, W, ctx && ctx->configured ? ctx->prm.num_disp : 64,
+                ctx && ctx->configured ? ctx->prm.zero_disp : 32, ctx && ctx->configured ? ctx->prm.usd : 17, &c));
+    cudaStream_t st = c->stream;
+    const size_t n = (size_t)H * W;
+    Tmp imgs, outs;
+    TRY(imgs.alloc(2 * n * 3));
+    TRY(outs.alloc(2 * n * 3));
+    uint8_t *in_l = imgs.as<uint8_t>(), *in_r = in_l + n * 3, *out_l = outs.as<uint8_t>(), *out_r = out_l + n * 3;
+    TRY(upload(in_l, img_in_l, n * 3, st));
+    TRY(upload(in_r, img_in_r, n * 3, st));
+    TRY(upload(c->dispF[0], disp_l, n * sizeof(float), st));
+    TRY(upload(c->dispF[1], disp_r, n * sizeof(float), st));
+    const dim3 g((W + 255) / 256, H);
+    const float shifts[2] = {shift, (float)(1.0 - (double)shift)};  // d_dibr_fwarp.cu:72: 1.0 - shift in double
+    const uint8_t *ins[2] = {in_l, in_r};
+    uint8_t *os[2] = {out_l, out_r};
+    for (int v = 0; v < 2; ++v) {
+        int *winner = c->irv_vote[v];  // an n-int scratch plane of the arena
+        CU(cudaMemsetAsync(winner, 0x7f, n * sizeof(int), st));  // 0x7f7f7f7f: above every column
+        k_fwarp_claim<<<g, 256, 0, st>>>(c->dispF[v], shifts[v], winner, H, W);
+        KCHECK();
+        k_fwarp_gather<<<g, 256, 0, st>>>(ins[v], winner, os[v], H, W);
+        KCHECK();
+    }
+    // dibr_occl_to_mask of a zeroed map (d_dibr_fwarp.cu:55-66): the mask is 0 everywhere
+    k_merge_ab<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out_l, out_r, nullptr, n);
+    KCHECK();
+    TRY(download(img_out, out_l, n * 3, st));
+    CU(cudaStreamSynchronize(st));
+    return S2MV_OK;
+}
+
 extern "C" int s2mv_mux_multiview(s2mv_ctx *ctx, uint8_t **views, uint8_t *out, int V, float angle, int Hin, int Win,
                                   int Hout, int Wout, int elem_sz, int kernel_variant)
 {
