@@ -128,16 +128,16 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr)
 // shared-memory carve-up of one CTA (every section 16-byte aligned); the kernel walks the same list
 __host__ __device__ inline size_t line2_align16(size_t b) { return (b + 15) & ~(size_t)15; }
 __host__ __device__ inline int line2_frame(int B, int HP) { return (B + 2 * HP + 1) & ~1; }  // mask positions per block
-__host__ __device__ inline size_t line2_smem_bytes(int S, int HP, int B, bool ci, int kL2Stages)
+__host__ __device__ inline size_t line2_smem_bytes(int S, int HP, int B, bool ci, int kL2Stages, int LP = 32)
 {
     const size_t P = (size_t)S + 2 * HP, NBT = (size_t)(S + B - 1) / B;
     size_t b = 128;                                                                     // alignment slack of the tile base
-    b += kL2Stages * P * kL2PosBytes;                                                   // tiles
+    b += kL2Stages * P * (size_t)(16 * LP);                                             // tiles
     b += 128;                                                                           // mbarriers
     b += line2_align16(kL2DescRing * sizeof(Line2Desc));                                // descriptors
     b += line2_align16((size_t)kL2DescRing * NBT * line2_frame(B, HP) * 2);             // window masks (u16)
     b += line2_align16((size_t)kL2DescRing * NBT * 4);                                  // walk bounds per block
-    b += line2_align16(kL2Stages * (ci ? (4 * P + 256) * 4 : 0)) + 80 * 4;              // operand words, census table
+    b += line2_align16(kL2Stages * (ci ? (4 * P + 8 * LP) * 4 : 0)) + 80 * 4;           // operand words, census table
     b += kL2DescRing * 4;                                                               // claimed runs (producer warps)
     return b;
 }
@@ -147,14 +147,14 @@ __host__ __device__ inline size_t line2_smem_bytes(int S, int HP, int B, bool ci
 // dbase..dbase+3 of the four positions (16 evaluations from 7 operand words, as ci_fill_tile), the argument
 // chain of the AD exponential on f32x2 pairs.  Columns 160m-1 / 160m replay the reference's flat indexing
 //  in place.
-template <bool PLUS, bool FULL_D>
+template <bool PLUS, bool FULL_D, int LP>
 __device__ __forceinline__ void ci_fill_groups2(float4 *__restrict__ C4, const uint32_t *__restrict__ sOwnP,
                                                 const uint32_t *__restrict__ sOwnC, const uint32_t *__restrict__ sOthP,
                                                 const uint32_t *__restrict__ sOthC, const float *__restrict__ sLutCen,
                                                 float inv_ad, int g_first, int g_step, int g_end, int q, int dbase,
                                                 const LineArgs &a, int view, int xb, size_t row)
 {
-    constexpr int LP = 32, Dc = 128;
+    constexpr int Dc = 4 * LP;
     const int D = a.D, W = a.W;
     bool dv[4];
 #pragma unroll
@@ -287,16 +287,16 @@ __device__ __forceinline__ void masks_from_arms(uint16_t *__restrict__ mrow, uin
 // ---------------------------------------------------------------- the window walk of one output block
 // tq: shared address of this lane's float4 of tile position 0; block outputs o0..o0+B-1; mrow: shared address
 // of the block's masks; bd: its walk bounds.
-template <int B>
-__device__ __forceinline__ void sum_block_masked(uint32_t tq, uint32_t mrow, uint32_t bd, int o0, float4 acc[B])
+template <int B, uint32_t PBY = kL2PosBytes>
+__device__ __forceinline__ void sum_block_span(uint32_t tq, uint32_t mrow, uint32_t first, uint32_t end, int o0, float4 acc[B])
 {
 #pragma unroll
     for (int i = 0; i < B; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const uint32_t first = bd & 0xffffu, end = bd >> 16;
-    uint32_t p = tq + ((uint32_t)o0 + first) * kL2PosBytes, mp = mrow + 2u * first;
-    const uint32_t pend = tq + ((uint32_t)o0 + end) * kL2PosBytes;
+    if (first >= end) return;
+    uint32_t p = tq + ((uint32_t)o0 + first) * PBY, mp = mrow + 2u * first;
+    const uint32_t n = end - first;
 #pragma unroll 4
-    for (; p != pend; p += kL2PosBytes, mp += 2) {
+    for (uint32_t k = 0; k < n; ++k, p += PBY, mp += 2) {
         const float4 v = lds128<0>(p);
         const uint32_t m = lds16(mp);
 #pragma unroll
@@ -304,16 +304,24 @@ __device__ __forceinline__ void sum_block_masked(uint32_t tq, uint32_t mrow, uin
             if (m & (2u << i)) acc4(acc[i], v);
     }
 }
+template <int B>
+__device__ __forceinline__ void sum_block_masked(uint32_t tq, uint32_t mrow, uint32_t bd, int o0, float4 acc[B])
+{
+    sum_block_span<B, kL2PosBytes>(tq, mrow, bd & 0xffffu, bd >> 16, o0, acc);
+}
 
 // ---------------------------------------------------------------- winner-takes-all of one output block
 // dc_wta_kernel (d_dc_wta.cu:9-35): strict '>' from FLT_MAX, first minimum wins.  Aggregated ADCensus costs are
 // >= +0, so their bit patterns order like the floats: lane minimum over its four disparities, CREDUX.MIN across
 // the warp, then CREDUX.MIN over the disparity indices of the lanes that hold the minimum.  Lane i keeps output
 // i's result; one store (or one atomicMin on (cost, d) keys when the disparity range spans several chunks).
-template <int B, bool FULL_D>
+template <int B, bool FULL_D, int LP = 32>
 __device__ __forceinline__ void wta_block(const float4 acc[B], const LineArgs &a, int vslot, int ln, int x0, int nvalid, int d0,
-                                          int lane)
+                                          int lane_in)
 {
+    // a pixel is the LP lanes of one sub-warp: the reductions run over that sub-warp only
+    const int lane = lane_in % LP;
+    const unsigned team = LP == 32 ? 0xffffffffu : (((1u << LP) - 1u) << ((lane_in / LP) * LP));
     const int dq = d0 + 4 * lane;
     uint32_t my_d = 0, my_m = 0;
 #pragma unroll
@@ -327,10 +335,10 @@ __device__ __forceinline__ void wta_block(const float4 acc[B], const LineArgs &a
             if (dq + 3 >= a.D) bw = 0xffffffffu;
         }
         const uint32_t lm = min(min(bx, by), min(bz, bw));
-        const uint32_t mn = __reduce_min_sync(0xffffffffu, lm);
+        const uint32_t mn = __reduce_min_sync(team, lm);
         const uint32_t j = bx == mn ? 0u : (by == mn ? 1u : (bz == mn ? 2u : 3u));
         const uint32_t cand = lm == mn ? (uint32_t)dq + j : 0x7fffffffu;
-        const uint32_t d = __reduce_min_sync(0xffffffffu, cand);
+        const uint32_t d = __reduce_min_sync(team, cand);
         if (lane == i) { my_d = d; my_m = mn; }
     }
     if (lane < nvalid) {
@@ -345,7 +353,10 @@ __device__ __forceinline__ void wta_block(const float4 acc[B], const LineArgs &a
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int MODE, int NW, int B, int NS>
+// LP = float4 lanes per pixel (32: one warp per pixel, 128 disparities per chunk; 16: two pixels per warp, num_disp <= 64).
+// With LP < 32 the sub-warps of a warp work on neighbouring blocks of the same tile, each lane with its own block's
+// masks, under one loop that spans the union of their walks.
+template <int MODE, int NW, int B, int NS, int LP = 32>
 __global__ void __launch_bounds__((NW + kL2Producers) * 32, 1)
 k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap tmap)
 {
@@ -354,24 +365,27 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
     constexpr bool CI = (MODE == LM_CI_H);
     const LineArgs &a = L.a;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int SUB = 32 / LP, Dc = 4 * LP;      // pixels per warp, disparities per chunk
+    constexpr uint32_t PBY = 16u * LP;              // bytes per tile position
+    const int sub = lane / LP, q = lane % LP;
     const int S = L.S, HP = L.HP, P = L.P, W = a.W;
 
     // ---- shared-memory carve-up (line2_smem_bytes); the tiles start on a 128-byte boundary (tensor copies)
     unsigned char *smem_raw = smem_l2 + ((128u - (smem_u32(smem_l2) & 127u)) & 127u);
-    const uint32_t tile_bytes = (uint32_t)P * kL2PosBytes;
+    const uint32_t tile_bytes = (uint32_t)P * PBY;
     unsigned char *sp = smem_raw + (size_t)NS * tile_bytes;
     const uint32_t bars = smem_u32(sp);  // [0..NS) full, then empty, fullO, emptyO (NS <= 4)
     sp += 128;
     Line2Desc *desc = reinterpret_cast<Line2Desc *>(sp);
     sp += line2_align16(kL2DescRing * sizeof(Line2Desc));
     const int FR = line2_frame(B, HP), NBT = (S + B - 1) / B;
-    constexpr int LPB = B <= 4 ? 4 : 8;  // producer lanes per block: up to 32 (short) or 16 blocks per tile
+    constexpr int LPB = (B <= 4 || LP < 32) ? 4 : 8;  // producer lanes per block: up to 32 or 16 blocks per tile
     uint16_t *sMask = reinterpret_cast<uint16_t *>(sp);  // [ring][block][frame position]
     sp += line2_align16((size_t)kL2DescRing * NBT * FR * 2);
     uint32_t *sBounds = reinterpret_cast<uint32_t *>(sp);  // [ring][block]
     sp += line2_align16((size_t)kL2DescRing * NBT * 4);
     uint32_t *sOps = reinterpret_cast<uint32_t *>(sp);  // CI: per stage ownP[P] ownC[P] othP[P+128] othC[P+128]
-    const int OPS = CI ? 4 * P + 256 : 0;
+    const int OPS = CI ? 4 * P + 2 * Dc : 0;
     float *sLutCen = reinterpret_cast<float *>(sp + line2_align16((size_t)NS * OPS * 4));
 
     auto full = [&](int s) { return bars + 8u * s; };
@@ -456,30 +470,30 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
                     const uint32_t dst = smem_u32(smem_raw) + (uint32_t)st * tile_bytes;
                     // several copies per tile: more requests of the copy engine in flight
                     for (int p0 = 0; p0 < P; p0 += L.tmap_rows) {
-                        if (VERT) tma_load_4d(dst + (uint32_t)p0 * kL2PosBytes, &tmap, chunk * 128, ln, t0 - HP - L.row_bias + p0, vslot, bar);
-                        else tma_load_4d(dst + (uint32_t)p0 * kL2PosBytes, &tmap, chunk * 128, t0 - HP + p0, ln - L.row_bias, vslot, bar);
+                        if (VERT) tma_load_4d(dst + (uint32_t)p0 * PBY, &tmap, chunk * Dc, ln, t0 - HP - L.row_bias + p0, vslot, bar);
+                        else tma_load_4d(dst + (uint32_t)p0 * PBY, &tmap, chunk * Dc, t0 - HP + p0, ln - L.row_bias, vslot, bar);
                     }
                 }
             }
             if (!CI && valid && !L.use_tmap && pw == 0) {
                 const int p_lo = max(0, IN_LO + HP - t0), p_hi = min(P, IN_HI - t0 + HP);
                 const int np = max(p_hi - p_lo, 0);
-                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)np * kL2PosBytes);
-                const size_t line_base4 = (VERT ? (size_t)ln * a.LPtot : (size_t)ln * W * a.LPtot) + (size_t)chunk * 32;
+                if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)np * PBY);
+                const size_t line_base4 = (VERT ? (size_t)ln * a.LPtot : (size_t)ln * W * a.LPtot) + (size_t)chunk * LP;
                 const char *src0 = reinterpret_cast<const char *>(a.in[vslot] + line_base4) +
                                    (long long)(t0 - HP + p_lo) * (long long)pos_stride4 * 16;
-                const uint32_t dst0 = smem_u32(smem_raw) + (uint32_t)st * tile_bytes + (uint32_t)p_lo * kL2PosBytes;
+                const uint32_t dst0 = smem_u32(smem_raw) + (uint32_t)st * tile_bytes + (uint32_t)p_lo * PBY;
                 const long long gs = (long long)pos_stride4 * 16;
                 for (int p = lane; p < np; p += 32)
-                    bulk_g2s(dst0 + (uint32_t)p * kL2PosBytes, src0 + (long long)p * gs, kL2PosBytes, bar);
+                    bulk_g2s(dst0 + (uint32_t)p * PBY, src0 + (long long)p * gs, PBY, bar);
             }
             if (valid && CI) {
                 const int view = a.view_first + vslot;
-                const int d0 = a.d_first + chunk * 128;
+                const int d0 = a.d_first + chunk * Dc;
                 const size_t row = (size_t)ln * W;
                 const int xb = t0 - HP;
                 // other-view words start at the column that makes every thread's 8-word window 16-byte aligned
-                const int xo = (view == 0) ? (xb - a.zd + d0) : (xb + a.zd - d0 - 128);
+                const int xo = (view == 0) ? (xb - a.zd + d0) : (xb + a.zd - d0 - Dc);
                 const uint32_t *gOwnP = (view == 0 ? a.pixL : a.pixR) + row, *gOwnC = (view == 0 ? a.cenL : a.cenR) + row;
                 const uint32_t *gOthP = (view == 0 ? a.pixR : a.pixL) + row, *gOthC = (view == 0 ? a.cenR : a.cenL) + row;
                 const uint32_t o0 = smem_u32(sOps + (size_t)st * OPS);
@@ -491,10 +505,10 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
                     cp_async4(o0 + 4u * i, gOwnP + x, 4u);
                     cp_async4(o0 + 4u * (P + i), gOwnC + x, 4u);
                 }
-                for (int i = i0 + pl; i < P + 128; i += 32 * kL2Producers) {
+                for (int i = i0 + pl; i < P + Dc; i += 32 * kL2Producers) {
                     const int x = clampi(xo + i, 0, W - 1);
                     cp_async4(o0 + 4u * (2 * P + i), gOthP + x, 4u);
-                    cp_async4(o0 + 4u * (3 * P + 128 + i), gOthC + x, 4u);
+                    cp_async4(o0 + 4u * (3 * P + Dc + i), gOthC + x, 4u);
                 }
             }
             if (CI) cp_async_arrive_noinc(bar);
@@ -528,7 +542,7 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
     }
 
     // =========================================================== consumer warps
-    const uint32_t tq0 = smem_u32(smem_raw) + (uint32_t)lane * 16u;
+    const uint32_t tq0 = smem_u32(smem_raw) + (uint32_t)q * 16u;
     const long long ostride = (long long)pos_stride4 * 16;
     float4 *const C4base = reinterpret_cast<float4 *>(smem_raw);
 
@@ -536,24 +550,24 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
         // consumer-side production of tile m (pass 1): operands -> 128 costs per position
         const int st = m % NS;
         const int view = a.view_first + d.vslot;
-        const int d0 = a.d_first + d.chunk * 128;
+        const int d0 = a.d_first + d.chunk * Dc;
         const uint32_t *ops = sOps + (size_t)st * OPS;
-        float4 *C4 = C4base + (size_t)st * P * 32;
+        float4 *C4 = C4base + (size_t)st * P * LP;
         int g_begin = 0;
         if (carry) {
             // positions [0, 2*HP) of this tile are positions [S, S + 2*HP) of the previous one
-            const float4 *src = C4base + (size_t)prev_stage * P * 32 + (size_t)S * 32;
-            for (int p = warp; p < 2 * HP; p += NW) C4[(size_t)p * 32 + lane] = src[(size_t)p * 32 + lane];
+            const float4 *src = C4base + (size_t)prev_stage * P * LP + (size_t)S * LP;
+            for (int p = warp * SUB + sub; p < 2 * HP; p += NW * SUB) C4[(size_t)p * LP + q] = src[(size_t)p * LP + q];
             g_begin = (2 * HP) / 4;
         }
-        const bool full_d = d0 + 128 <= a.D;
+        const bool full_d = d0 + Dc <= a.D;
         const size_t row = (size_t)d.ln * W;
         const int xb = d.t0 - HP;
         // rotate the first group among the warps so that a longer first tile does not always load warp 0
-        const int g_first = g_begin + ((warp + m) % NW);
-#define S2MV_L2_FILL(PLUS, FULL)                                                                                      \
-    ci_fill_groups2<PLUS, FULL>(C4, ops, ops + P, ops + 2 * P, ops + 3 * P + 128, sLutCen, a.inv_ad, g_first, NW, P / 4, \
-                                lane, d0 + 4 * lane, a, view, xb, row)
+        const int g_first = g_begin + ((warp + m) % NW) * SUB + sub;
+#define S2MV_L2_FILL(PLUS, FULL)                                                                                             \
+    ci_fill_groups2<PLUS, FULL, LP>(C4, ops, ops + P, ops + 2 * P, ops + 3 * P + Dc, sLutCen, a.inv_ad, g_first, NW * SUB, P / 4, \
+                                    q, d0 + 4 * q, a, view, xb, row)
         if (view == 0) { if (full_d) S2MV_L2_FILL(true, true); else S2MV_L2_FILL(true, false); }
         else           { if (full_d) S2MV_L2_FILL(false, true); else S2MV_L2_FILL(false, false); }
 #undef S2MV_L2_FILL
@@ -583,16 +597,24 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
         }
 
         const int vslot = d.vslot, chunk = d.chunk, ln = d.ln, t0 = d.t0, Sact = d.Sact;
-        const int d0 = a.d_first + chunk * 128;
-        const bool full_d = d0 + 128 <= a.D;
+        const int d0 = a.d_first + chunk * Dc;
+        const bool full_d = d0 + Dc <= a.D;
         const uint32_t tq = tq0 + (uint32_t)st * tile_bytes;
-        const size_t line_base4 = (VERT ? (size_t)ln * a.LPtot : (size_t)ln * W * a.LPtot) + (size_t)chunk * 32 + lane;
+        const size_t line_base4 = (VERT ? (size_t)ln * a.LPtot : (size_t)ln * W * a.LPtot) + (size_t)chunk * LP + q;
         const int nblocks = (Sact + B - 1) / B;
         const bool has_peer = MODE != LM_H_WTA && (a.peer_out[0][vslot] != nullptr || a.peer_out[1][vslot] != nullptr);
-        for (int b = warp; b < nblocks; b += NW) {
-            const int o0 = b * B, nvalid = min(B, Sact - o0);
+        for (int b0 = warp * SUB; b0 < nblocks; b0 += NW * SUB) {
+            // this lane's block (every sub-warp its own; NBT is a multiple of SUB, blocks past the line end have empty masks)
+            const int b = b0 + sub;
+            const int o0 = b * B, nvalid = max(0, min(B, Sact - o0));
             float4 acc[B];
-            sum_block_masked<B>(tq, smem_u32(sMask + ((size_t)ring * NBT + b) * FR), sBounds[ring * NBT + b], o0, acc);
+            const uint32_t bd = sBounds[ring * NBT + b];
+            uint32_t first = bd ? (bd & 0xffffu) : 0xffffu, end = bd >> 16;
+            if (SUB > 1) {  // one loop over the union of the sub-warps' walks; a lane's masks are 0 outside its own
+                first = __reduce_min_sync(0xffffffffu, first);
+                end = __reduce_max_sync(0xffffffffu, end);
+            }
+            sum_block_span<B, PBY>(tq, smem_u32(sMask + ((size_t)ring * NBT + b) * FR), first, end, o0, acc);
             if (MODE != LM_H_WTA) {
                 char *dstp = reinterpret_cast<char *>(a.out[vslot] + line_base4) + (long long)(t0 + o0) * ostride;
 #pragma unroll
@@ -610,8 +632,8 @@ k_line2(const __grid_constant__ Line2Args L, const __grid_constant__ CUtensorMap
                     }
                 }
             } else {
-                if (full_d) wta_block<B, true>(acc, a, vslot, ln, t0 + o0, nvalid, d0, lane);
-                else wta_block<B, false>(acc, a, vslot, ln, t0 + o0, nvalid, d0, lane);
+                if (full_d) wta_block<B, true, LP>(acc, a, vslot, ln, t0 + o0, nvalid, d0, lane);
+                else wta_block<B, false, LP>(acc, a, vslot, ln, t0 + o0, nvalid, d0, lane);
             }
         }
         if (!CI) {

@@ -145,13 +145,13 @@ struct L2Cfg { int NW, B, NS; };
 static const L2Cfg kL2Cfg[3][2] = {{{16, 6, 3}, {12, 8, 3}}, {{16, 4, 4}, {16, 4, 4}}, {{16, 6, 3}, {12, 4, 3}}};  // [cfg][0 loaded, 1 computed]
 
 // outputs per tile along a line of `len` outputs: close to NW * B, a multiple of the block size, the line cut evenly
-static int line2_segment(int len, int B, int NW)
+static int line2_segment(int len, int B, int NW, int SUB = 1)
 {
-    const int full = NW * B;
+    const int unit = B * SUB, full = NW * unit;  // a warp works on SUB blocks at a time
     const int nseg = (len + full - 1) / full;
     int S = (len + nseg - 1) / nseg;
-    S = ((S + B - 1) / B) * B;
-    return S < B ? B : S;
+    S = ((S + unit - 1) / unit) * unit;
+    return S < unit ? unit : S;
 }
 
 static size_t hpass_smem(int S, int halo, int Dc, int M, bool ci)
@@ -235,23 +235,27 @@ static int make_plan(CostPlan &pl, int H, int W, int D, int zd, int usd, int l2_
     // persistent pipelined line kernel: one warp per pixel (128 disparities per chunk), three tiles per SM
     pl.line2 = false;
     pl.vv = false;
-    if (pl.LP == 32) {
+    if (pl.LP == 32 || pl.LP == 16) {
+        // LP = 16 (num_disp <= 64): two pixels per warp, tiles twice as long (same bytes); configuration 0 only
+        if (pl.LP == 16) l2_cfg = 0;
+        const int SUB = 32 / pl.LP;
         pl.l2_cfg = l2_cfg;
         const L2Cfg &ld = kL2Cfg[l2_cfg][0], &ci = kL2Cfg[l2_cfg][1];
         pl.l2_HP = (usd + 1) & ~1;
-        pl.l2_S_ci = l2_cfg == 2 ? line2_segment(W, 8, 12) : line2_segment(W, ci.B, ci.NW);
-        pl.l2_S_h = line2_segment(W, ld.B, ld.NW);
-        pl.l2_S_v = line2_segment(H, ld.B, ld.NW);
-        pl.l2_smem_ci = line2_smem_bytes(pl.l2_S_ci, pl.l2_HP, ci.B, true, ci.NS);
-        pl.l2_smem_h = line2_smem_bytes(pl.l2_S_h, pl.l2_HP, ld.B, false, ld.NS);
-        pl.l2_smem_v = line2_smem_bytes(pl.l2_S_v, pl.l2_HP, ld.B, false, ld.NS);
+        pl.l2_S_ci = l2_cfg == 2 ? line2_segment(W, 8, 12) : line2_segment(W, ci.B, ci.NW, SUB);
+        pl.l2_S_h = line2_segment(W, ld.B, ld.NW, SUB);
+        pl.l2_S_v = line2_segment(H, ld.B, ld.NW, SUB);
+        pl.l2_smem_ci = line2_smem_bytes(pl.l2_S_ci, pl.l2_HP, ci.B, true, ci.NS, pl.LP);
+        pl.l2_smem_h = line2_smem_bytes(pl.l2_S_h, pl.l2_HP, ld.B, false, ld.NS, pl.LP);
+        pl.l2_smem_v = line2_smem_bytes(pl.l2_S_v, pl.l2_HP, ld.B, false, ld.NS, pl.LP);
         const size_t cap = 227 * 1024;
-        pl.line2 = pl.l2_smem_ci <= cap && pl.l2_smem_h <= cap && pl.l2_smem_v <= cap;
+        pl.line2 = pl.l2_smem_ci <= cap && pl.l2_smem_h <= cap && pl.l2_smem_v <= cap &&
+                   pl.l2_S_ci / ci.B <= kL2MaxBlocks && pl.l2_S_h / ld.B <= kL2MaxBlocks && pl.l2_S_v / ld.B <= kL2MaxBlocks;
         pl.vv_HP = ((usd + kVVB - 1) / kVVB) * kVVB;
         if (pl.vv_HP < kVVB) pl.vv_HP = kVVB;
         pl.vv_S = kVVNA * kVVB;
         pl.vv_smem = linevv_smem_bytes<kVVNA, kVVB>(pl.vv_S, pl.vv_HP);
-        pl.vv = pl.line2 && pl.vv_smem <= cap;
+        pl.vv = pl.line2 && pl.LP == 32 && pl.vv_smem <= cap;
     }
     return S2MV_OK;
 }
@@ -528,6 +532,10 @@ static int set_kernel_attrs()
     TRY((set_smem(k_line2<LM_CI_H, 16, 4, 4>, big)));
     TRY((set_smem(k_line2<LM_CI_H, 12, 4, 3>, big)));
     TRY((set_line2_attrs<16, 6, 3>()));
+    TRY((set_smem(k_line2<LM_CI_H, 12, 8, 3, 16>, big)));
+    TRY((set_smem(k_line2<LM_H, 16, 6, 3, 16>, big)));
+    TRY((set_smem(k_line2<LM_H_WTA, 16, 6, 3, 16>, big)));
+    TRY((set_smem(k_line2<LM_V, 16, 6, 3, 16>, big)));
     TRY((set_line2_attrs<16, 4, 4>()));
     TRY(set_smem(k_bilateral, 160 * 1024));
     TRY(set_smem(k_bilateral4<7, true>, 64 * 1024));
@@ -631,7 +639,7 @@ static bool make_volume_tmaps(s2mv_ctx *c, size_t vol_rows)
             const int Pfull = (vert ? pl.l2_S_v : pl.l2_S_h) + 2 * pl.l2_HP;
             const cuuint32_t P = (cuuint32_t)tmap_split_rows(Pfull, c->env_tmap_rows);
             c->tmap_rows[vert] = (int)P;
-            const cuuint32_t box[4] = {128, vert ? 1u : P, vert ? P : 1u, 1};
+            const cuuint32_t box[4] = {(cuuint32_t)(4 * pl.LP), vert ? 1u : P, vert ? P : 1u, 1};
             CUresult r = enc(&c->tmap_vol[buf][vert], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, c->vol[buf], gdim, gstr, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -943,7 +951,14 @@ static int launch_pass(s2mv_ctx *c, LineArgs a, int pass, float4 *A, float4 *B, 
         const int mode = ci ? LM_CI_H : (vert ? LM_V : ((pass == 4 && to_wta) ? LM_H_WTA : LM_H));
         const size_t smem = ci ? pl.l2_smem_ci : (vert ? pl.l2_smem_v : pl.l2_smem_h);
 #define S2MV_L2_LAUNCH(MODE, NW, B, NS) k_line2<MODE, NW, B, NS><<<grid, (NW + kL2Producers) * 32, smem, st>>>(L, tm)
-        if (pl.l2_cfg != 1) {
+        if (pl.LP == 16) {
+#define S2MV_L2_LAUNCH16(MODE, NW, B, NS) k_line2<MODE, NW, B, NS, 16><<<grid, (NW + kL2Producers) * 32, smem, st>>>(L, tm)
+            if (mode == LM_CI_H) S2MV_L2_LAUNCH16(LM_CI_H, 12, 8, 3);
+            else if (mode == LM_V) S2MV_L2_LAUNCH16(LM_V, 16, 6, 3);
+            else if (mode == LM_H_WTA) S2MV_L2_LAUNCH16(LM_H_WTA, 16, 6, 3);
+            else S2MV_L2_LAUNCH16(LM_H, 16, 6, 3);
+#undef S2MV_L2_LAUNCH16
+        } else if (pl.l2_cfg != 1) {
             if (mode == LM_CI_H && pl.l2_cfg == 2) S2MV_L2_LAUNCH(LM_CI_H, 12, 4, 3);
             else if (mode == LM_CI_H) S2MV_L2_LAUNCH(LM_CI_H, 12, 8, 3);
             else if (mode == LM_V) S2MV_L2_LAUNCH(LM_V, 16, 6, 3);
