@@ -140,9 +140,10 @@ struct CostPlan {
 //   cfg 0: loaded-tile passes 16 x 6, 3 stages of ~96 outputs;  pass 1 (tiles are computed) 12 x 8, 3 stages
 //   cfg 1: every pass 16 x 4, 4 stages of ~64 outputs (one more tile in flight, shorter blocks)
 //   cfg 2: as cfg 0, but pass 1 sums blocks of 4 outputs, two per warp (96 outputs per tile)
+//   cfg 3: as cfg 0, but the loaded-tile passes run 24 consumer warps x 4-output blocks (96 outputs per tile)
 constexpr int kVVNA = 8, kVVB = 6;   // k_line_vv: 8 + 8 consumer warps, 6 rows per block, 48 rows per tile
 struct L2Cfg { int NW, B, NS; };
-static const L2Cfg kL2Cfg[3][2] = {{{16, 6, 3}, {12, 8, 3}}, {{16, 4, 4}, {16, 4, 4}}, {{16, 6, 3}, {12, 4, 3}}};  // [cfg][0 loaded, 1 computed]
+static const L2Cfg kL2Cfg[4][2] = {{{16, 6, 3}, {12, 8, 3}}, {{16, 4, 4}, {16, 4, 4}}, {{16, 6, 3}, {12, 4, 3}}, {{24, 4, 3}, {12, 8, 3}}};  // [cfg][0 loaded, 1 computed]
 
 // outputs per tile along a line of `len` outputs: close to NW * B, a multiple of the block size, the line cut evenly
 static int line2_segment(int len, int B, int NW, int SUB = 1)
@@ -343,6 +344,10 @@ struct s2mv_ctx {
     bool env_bilateral_scalar = false;  // S2MV_BILATERAL_SCALAR
     bool env_line_v1 = false;           // S2MV_LINE_V1: the first form of the cost-volume kernel (k_line) for every plan
     int env_l2_cfg = 0;                 // S2MV_L2_CFG: k_line2 configuration (kL2Cfg)
+    // S2MV_VOL_PAD: byte offset of the second volume inside its allocation (multiple of 512).  Measured at 1080p D=128 with
+    // the vertical passes as two launches: 0.87 ms per pass at offsets 0 ... 1 MB and 16 MB, 0.765 ms at 3 MB and 1 GB
+    // (the read and the write stream of a pass then fall on different DRAM channels at the same time).
+    long long env_vol_pad = 3 << 20;
     bool env_line_bulk = false;         // S2MV_LINE_BULK: k_line2 with per-position bulk copies instead of the tensor map
     int *line_ctr = nullptr;            // k_line2 work counters, one per pass
     CUtensorMap tmap_vol[2][2];         // tensor maps of the ping-pong volumes: [buffer A/B][row tile / column tile]
@@ -446,8 +451,9 @@ extern "C" int s2mv_create(s2mv_ctx **out, int device)
     if (const char *e = getenv("S2MV_IRV_DENSE_MIN")) c->env_irv_dense_min = atoi(e) < 0 ? 0 : atoi(e);
     if (const char *e = getenv("S2MV_BILATERAL_SCALAR")) c->env_bilateral_scalar = atoi(e) != 0;
     if (const char *e = getenv("S2MV_LINE_V1")) c->env_line_v1 = atoi(e) != 0;
-    if (const char *e = getenv("S2MV_L2_CFG")) c->env_l2_cfg = std::min(2, std::max(0, atoi(e)));
+    if (const char *e = getenv("S2MV_L2_CFG")) c->env_l2_cfg = std::min(3, std::max(0, atoi(e)));
     if (const char *e = getenv("S2MV_NO_VV")) c->env_no_vv = atoi(e) != 0;
+    if (const char *e = getenv("S2MV_VOL_PAD")) c->env_vol_pad = (std::max(0LL, atoll(e)) / 512) * 512;
     if (const char *e = getenv("S2MV_TMAP_ROWS")) c->env_tmap_rows = std::max(1, atoi(e));
     if (const char *e = getenv("S2MV_LINE_BULK")) c->env_line_bulk = atoi(e) != 0;
     if (const char *e = getenv("S2MV_BAND_WAIT_SPINS")) c->env_band_wait_spins = atoll(e) > 0 ? atoll(e) : 1;
@@ -537,6 +543,7 @@ static int set_kernel_attrs()
     TRY((set_smem(k_line2<LM_H_WTA, 16, 6, 3, 16>, big)));
     TRY((set_smem(k_line2<LM_V, 16, 6, 3, 16>, big)));
     TRY((set_line2_attrs<16, 4, 4>()));
+    TRY((set_line2_attrs<24, 4, 3>()));
     TRY(set_smem(k_bilateral, 160 * 1024));
     TRY(set_smem(k_bilateral4<7, true>, 64 * 1024));
     TRY(set_smem(k_bilateral4<7, false>, 64 * 1024));
@@ -726,7 +733,13 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
         TRY(dev_alloc_t(c, &c->tap_irv[v], n));
         TRY(dev_alloc_t(c, &c->tap_outl[v], n));
         if (pl.nchunks > 1) TRY(dev_alloc_t(c, &c->wta_key[v], n));
-        TRY(dev_alloc_t(c, &c->vol[v], vol_elems));
+        {   // the second ping-pong volume starts S2MV_VOL_PAD bytes into its allocation (the passes read one
+            // volume and write the other at the same offsets; their relative placement decides how the two streams fall on
+            // the DRAM channels)
+            const size_t pad = (v == 1 && !band) ? (size_t)c->env_vol_pad / sizeof(float) : 0;  // bands export allocation bases
+            TRY(dev_alloc_t(c, &c->vol[v], vol_elems + pad));
+            c->vol[v] += pad;
+        }
     }
     {   // dense region voting: one byte per (pixel, histogram bin); skipped when it would crowd the device
         const int nbins = p->num_disp > 65 ? p->num_disp : 65, nbp = ((nbins + 127) / 128) * 128;
@@ -958,6 +971,10 @@ static int launch_pass(s2mv_ctx *c, LineArgs a, int pass, float4 *A, float4 *B, 
             else if (mode == LM_H_WTA) S2MV_L2_LAUNCH16(LM_H_WTA, 16, 6, 3);
             else S2MV_L2_LAUNCH16(LM_H, 16, 6, 3);
 #undef S2MV_L2_LAUNCH16
+        } else if (pl.l2_cfg == 3 && mode != LM_CI_H) {
+            if (mode == LM_V) S2MV_L2_LAUNCH(LM_V, 24, 4, 3);
+            else if (mode == LM_H_WTA) S2MV_L2_LAUNCH(LM_H_WTA, 24, 4, 3);
+            else S2MV_L2_LAUNCH(LM_H, 24, 4, 3);
         } else if (pl.l2_cfg != 1) {
             if (mode == LM_CI_H && pl.l2_cfg == 2) S2MV_L2_LAUNCH(LM_CI_H, 12, 4, 3);
             else if (mode == LM_CI_H) S2MV_L2_LAUNCH(LM_CI_H, 12, 8, 3);
