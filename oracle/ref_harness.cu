@@ -98,11 +98,16 @@ void ref_dibr_dbm(unsigned char *img_out, unsigned char *img_in_l, unsigned char
              num_rows, num_cols, elem_sz);
 }
 
-/* d_dibr_fwarp.h:18-21 (never called by the reference's drivers; racy where sources collide) */
+/* d_dibr_fwarp.h:18-21 (never called by the reference's drivers; racy where sources collide).
+ * dibr_dfm frees d_img_out_r twice (d_dibr_fwarp.cu:186,193): the second cudaFree leaves cudaErrorInvalidValue as the
+ * runtime's last error, which any other user of the same libcudart in the process (torch) would trip over -- it is
+ * read and dropped here. */
 void ref_dibr_dfm(unsigned char *img_out, unsigned char *img_in_l, unsigned char *img_in_r, float *disp_l, float *disp_r,
                   float shift, int num_rows, int num_cols, int elem_sz)
 {
     dibr_dfm(img_out, img_in_l, img_in_r, disp_l, disp_r, shift, num_rows, num_cols, elem_sz);
+    cudaDeviceSynchronize();
+    cudaGetLastError();
 }
 
 void ref_mux_multiview(unsigned char **views, unsigned char *out, int num_views, float angle,
