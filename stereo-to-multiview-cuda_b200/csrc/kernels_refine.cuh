@@ -67,7 +67,12 @@ struct IrvArgs {
     // hchg[pixel] = the pixel's horizontal span holds a pixel changed by the previous iteration
     uint8_t *stamp[2];
     uint8_t *hchg[2];
+    // rows voted in this iteration, [row_lo, row_hi): the whole image, or -- in a row band -- the band's own rows plus
+    // what the remaining iterations and the filters after them can still carry into the own rows (s2mv_api.cu)
+    int row_lo, row_hi;
     int dense_min;       // list length from which an iteration takes the dense path
+    int col_votes;       // > 0: dense iterations vote column by column (k_irv_vote_col), this many columns (1..4) per
+                         // ticket; vote[] is then indexed by PIXEL
 };
 constexpr int kNoVote = -0x7fffffff;
 
@@ -146,6 +151,10 @@ k_irv_vote(const IrvArgs a)
     for (int e = blockIdx.x * kIrvWarps + warp; e < count; e += gridDim.x * kIrvWarps) {
         const int pix = a.list[v][e];
         const int gy = pix / W, gx = pix - gy * W;
+        if (gy < a.row_lo || gy >= a.row_hi) {  // not voted in this iteration (row band: cannot reach the own rows any more)
+            if (lane == 0) a.vote[v][e] = kNoVote;
+            continue;
+        }
         for (int b = lane; b < a.nbins; b += 32) hist[b] = 0;
         __syncwarp();
         const uint32_t ac = arms[pix];
@@ -248,6 +257,7 @@ k_irv_hseg(const IrvArgs a)
     uint32_t *hw = reinterpret_cast<uint32_t *>(hs);
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int gy = tile / tiles_x, bx = (tile - gy * tiles_x) * kHsegThreads;
+        if (gy < a.row_lo - a.usd || gy >= a.row_hi + a.usd) continue;  // no voted outlier reads this row (block-uniform)
         const int gx = bx + t;
         const size_t row = (size_t)gy * W;
         int mine = 1;  // this pixel's histogram has to be (re)built
@@ -328,6 +338,10 @@ k_irv_vote_dense(const IrvArgs a)
         }
         const int pix = a.list[v][e];
         const int gy = pix / W, gx = pix - gy * W;
+        if (gy < a.row_lo || gy >= a.row_hi) {  // not voted in this iteration
+            if (lane == 0) a.vote[v][e] = kNoVote;
+            continue;
+        }
         const uint32_t ac = arms[pix];
         const int cu = min(arm_up(ac), a.usd), nrows = cu + arm_down(ac) + 1;  // rows [-cu, +cd] inclusive
         if (a.it > 0 && a.stamp[v] != nullptr) {
@@ -378,6 +392,176 @@ k_irv_vote_dense(const IrvArgs a)
     }
 }
 
+// ---- dense path, column walk -------------------------------------------------
+// k_irv_vote_dense adds up to 2*usd+1 span histograms per outlier, and vertically adjacent outliers of a column add
+// almost the same ones: their vertical arms end at the same colour edge (or both at usd rows, one row apart).  Here a
+// warp owns a 32 x 32 pixel tile and walks each of its columns downwards with the histogram of the current row window
+// in registers; the next outlier's window is reached by adding the rows that enter and subtracting the rows that leave
+// (packed 16-bit fields: a row that leaves was added before, so no field borrows), or rebuilt when that is cheaper.
+// An occluded region then costs about two 128-byte row reads per outlier instead of its arm length; sums of integer
+// counts, so the histogram -- and with it count, first maximum and vote -- is the one k_irv_vote_dense forms.
+// Votes are stored per PIXEL (k_irv_apply reads them there when col_votes is set).
+template <int NW>
+__global__ void __launch_bounds__(kIrvWarps * 32)
+k_irv_vote_col(const IrvArgs a)
+{
+    const int v = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    if (irv_settled(a, v)) return;
+    const int count = *a.count[v];
+    if (count < a.dense_min) return;
+    const float *__restrict__ disp = a.disp[v];
+    const uint8_t *__restrict__ outl = a.outliers[v];
+    const uint32_t *__restrict__ arms = a.arms[v];
+    const uint8_t *__restrict__ hchg = a.hchg[v];
+    const uint32_t *__restrict__ hseg = reinterpret_cast<const uint32_t *>(a.hseg[v]);
+    int *__restrict__ vote = a.vote[v];
+    const int W = a.W, H = a.H, usd = a.usd;
+    constexpr int WPP = 32 * NW;  // 32-bit words per pixel
+    const bool incremental = a.it > 0 && a.stamp[v] != nullptr;
+    // a ticket = kColW adjacent columns of a 32-row strip; strips in raster order, so the warps in flight sit on
+    // neighbouring columns of the same rows (their flag, arm and histogram reads share sectors and L2 lines)
+    const int kColW = a.col_votes;
+    const int tiles_x = (W + kColW - 1) / kColW, tiles_y = (a.row_hi - a.row_lo + 31) / 32, ntiles = tiles_x * tiles_y;
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = atomicAdd(a.ticket[v], 1);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= ntiles) break;
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int xs = tx * kColW, ys = a.row_lo + ty * 32;
+        const int y_l = ys + lane;                      // lane <-> row of the strip
+        const bool row_ok = y_l < a.row_hi;
+        const int ncol = min(kColW, W - xs);
+        // outlier flags: bit j of `orow` = pixel (y_l, xs + j)
+        uint32_t orow = 0;
+        if (row_ok) {
+            const uint8_t *op = outl + (size_t)y_l * W + xs;
+            if (ncol == 4 && ((uintptr_t)op & 3) == 0) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(op);
+                const uint32_t hb = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;  // non-zero bytes
+                orow = ((hb >> 7) & 1u) | ((hb >> 14) & 2u) | ((hb >> 21) & 4u) | ((hb >> 28) & 8u);
+            } else {
+                for (int j = 0; j < ncol; ++j) orow |= (op[j] != 0 ? 1u : 0u) << j;
+            }
+        }
+        if (!__any_sync(0xffffffffu, orow != 0)) continue;
+        for (int j = 0; j < ncol; ++j) {
+            uint32_t m = __ballot_sync(0xffffffffu, (orow >> j) & 1u);  // bit i: (ys + i, gx) is an outlier
+            if (m == 0) continue;
+            const int gx = xs + j;
+            const uint32_t arm_l = row_ok ? arms[(size_t)y_l * W + gx] : 0u;
+            // rows of this column whose span changed in the previous iteration, [ys - usd, ys + 32 + usd): bit r of word k
+            uint32_t chg[5] = {0u, 0u, 0u, 0u, 0u};
+            if (incremental) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const int r = ys - usd + 32 * k + lane;
+                    const bool in = 32 * k < 32 + 2 * usd && r >= 0 && r < H;
+                    chg[k] = __ballot_sync(0xffffffffu, in && hchg[(size_t)r * W + gx] != 0);
+                }
+            }
+            uint32_t lo[NW], hi[NW];  // 16-bit fields: bins (0, 2) and (1, 3) of each packed word
+#pragma unroll
+            for (int w = 0; w < NW; ++w) lo[w] = hi[w] = 0u;
+            int wlo = 0, whi = -1;  // rows in the window, inclusive; empty
+            const uint32_t *__restrict__ col = hseg + (size_t)gx * WPP + lane;
+            const size_t rstride = (size_t)W * WPP;
+            while (m) {
+                const int i = __ffs(m) - 1;
+                m &= m - 1;
+                const int gy = ys + i;
+                const uint32_t ac = __shfl_sync(0xffffffffu, arm_l, i);
+                const int nlo = gy - min(arm_up(ac), usd), nhi = gy + arm_down(ac);
+                if (incremental) {
+                    // still listed = its last vote was rejected; with no changed span in its support it would be again
+                    const int b0 = nlo - (ys - usd), b1 = nhi - (ys - usd);  // bit range, inclusive
+                    uint32_t hit = 0;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const int s0 = max(b0 - 32 * k, 0), s1 = min(b1 - 32 * k, 31);
+                        if (s0 <= s1) hit |= chg[k] & ((0xffffffffu >> (31 - s1)) & (0xffffffffu << s0));
+                    }
+                    if (!hit) {
+                        if (lane == 0) vote[(size_t)gy * W + gx] = kNoVote;
+                        continue;
+                    }
+                }
+                const int nrows = nhi - nlo + 1;
+                const bool slide = whi >= wlo && abs(nlo - wlo) + abs(nhi - whi) < nrows;
+                if (!slide) {
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) lo[w] = hi[w] = 0u;
+                    wlo = nlo;
+                    whi = nlo - 1;
+                }
+                // rows that leave (above the new top / below the new bottom), then rows that enter
+                for (; wlo < nlo; ++wlo) {
+                    const uint32_t *p = col + (size_t)wlo * rstride;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        const uint32_t x = __ldg(p + 32 * w);
+                        lo[w] -= x & 0x00ff00ffu;
+                        hi[w] -= (x >> 8) & 0x00ff00ffu;
+                    }
+                }
+                for (; whi > nhi; --whi) {
+                    const uint32_t *p = col + (size_t)whi * rstride;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        const uint32_t x = __ldg(p + 32 * w);
+                        lo[w] -= x & 0x00ff00ffu;
+                        hi[w] -= (x >> 8) & 0x00ff00ffu;
+                    }
+                }
+                for (; wlo > nlo;) {
+                    --wlo;
+                    const uint32_t *p = col + (size_t)wlo * rstride;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        const uint32_t x = __ldg(p + 32 * w);
+                        lo[w] += x & 0x00ff00ffu;
+                        hi[w] += (x >> 8) & 0x00ff00ffu;
+                    }
+                }
+#pragma unroll 4
+                for (; whi < nhi;) {
+                    ++whi;
+                    const uint32_t *p = col + (size_t)whi * rstride;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) {
+                        const uint32_t x = __ldg(p + 32 * w);
+                        lo[w] += x & 0x00ff00ffu;
+                        hi[w] += (x >> 8) & 0x00ff00ffu;
+                    }
+                }
+                // total count; first bin holding the maximum count: maximise (count, -bin).  An all-zero histogram gives
+                // a key with count 0 (best == 0 below); the four fields of a lane add up without leaving 16 bits
+                uint32_t cnt = 0, key = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const uint32_t c[4] = {lo[w] & 0xffffu, hi[w] & 0xffffu, lo[w] >> 16, hi[w] >> 16};
+                    const uint32_t s2 = lo[w] + hi[w];
+                    cnt += (s2 & 0xffffu) + (s2 >> 16);
+                    const uint32_t inv = 1023u - (uint32_t)(128 * w + 4 * lane);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) key = max(key, c[q] * 1024u + (inv - q));
+                }
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
+                key = __reduce_max_sync(0xffffffffu, key);
+                if (lane == 0) {
+                    const size_t pix = (size_t)gy * W + gx;
+                    const int best = (int)(key >> 10), bestb = 1023 - (int)(key & 1023u);
+                    int max_d = (best > 0) ? (bestb - a.zd) : (int)disp[pix];
+                    // dr_irv_kernel_3: ratio test on the histogram INDEX (Q16)
+                    bool ok = (int)cnt > a.thresh_s && __fdiv_rn((float)(max_d + a.zd), (float)(int)cnt) > a.thresh_h;
+                    vote[pix] = ok ? max_d : kNoVote;
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_irv_apply(const IrvArgs a)
 {
@@ -386,13 +570,20 @@ k_irv_apply(const IrvArgs a)
     const int count = *a.count[v];
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.ticket[v] = 0;  // for the next iteration's vote
     const int stride = gridDim.x * blockDim.x;
+    // this iteration's votes came from k_irv_vote_col: stored per pixel, for the rows it walked
+    const bool by_pixel = a.col_votes && a.hseg[v] && count >= a.dense_min;
     int taken = 0;
     for (int e0 = blockIdx.x * blockDim.x; e0 < count; e0 += stride) {  // block-uniform trip count
         const int e = e0 + threadIdx.x;
         int pix = -1;
         if (e < count) {
-            const int vote = a.vote[v][e];
             pix = a.list[v][e];
+            int vote = kNoVote;
+            if (!by_pixel) {
+                vote = a.vote[v][e];
+            } else if (pix >= a.row_lo * a.W && pix < a.row_hi * a.W) {
+                vote = a.vote[v][pix];
+            }
             if (vote != kNoVote) {
                 a.outliers[v][pix] = 0;
                 a.disp[v][pix] = (float)vote;

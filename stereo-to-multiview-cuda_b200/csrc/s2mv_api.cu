@@ -341,6 +341,8 @@ struct s2mv_ctx {
     const void *host_last[4] = {};  // the previous synchronous call's four caller buffers (auto mode)
     // test / A-B hooks read from the environment once, at create time
     int env_irv_dense_min = -1;     // S2MV_IRV_DENSE_MIN (-1: not set)
+    int env_irv_colw = 1;           // S2MV_IRV_COLW: columns per ticket of k_irv_vote_col (1..4; 1 measured best)
+    bool env_irv_list_votes = false; // S2MV_IRV_LIST_VOTES: dense iterations vote per list entry (k_irv_vote_dense), not per column
     bool env_bilateral_scalar = false;  // S2MV_BILATERAL_SCALAR
     bool env_line_v1 = false;           // S2MV_LINE_V1: the first form of the cost-volume kernel (k_line) for every plan
     int env_l2_cfg = 0;                 // S2MV_L2_CFG: k_line2 configuration (kL2Cfg)
@@ -449,6 +451,8 @@ extern "C" int s2mv_create(s2mv_ctx **out, int device)
     CU(cudaSetDevice(device));
     s2mv_ctx *c = new s2mv_ctx();
     if (const char *e = getenv("S2MV_IRV_DENSE_MIN")) c->env_irv_dense_min = atoi(e) < 0 ? 0 : atoi(e);
+    if (const char *e = getenv("S2MV_IRV_LIST_VOTES")) c->env_irv_list_votes = atoi(e) != 0;
+    if (const char *e = getenv("S2MV_IRV_COLW")) c->env_irv_colw = std::min(4, std::max(1, atoi(e)));
     if (const char *e = getenv("S2MV_BILATERAL_SCALAR")) c->env_bilateral_scalar = atoi(e) != 0;
     if (const char *e = getenv("S2MV_LINE_V1")) c->env_line_v1 = atoi(e) != 0;
     if (const char *e = getenv("S2MV_L2_CFG")) c->env_l2_cfg = std::min(3, std::max(0, atoi(e)));
@@ -1153,8 +1157,11 @@ static int launch_dcc(s2mv_ctx *c, const float *dL, const float *dR, uint8_t *oL
 // nviews = 1 or 2 views voted together; arrays indexed by view slot
 static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2], const uint32_t *const arms[2],
                       int nviews, int H, int W, int D, int zd, int usd, int thresh_s, float thresh_h, int iterations,
-                      cudaStream_t st)
+                      cudaStream_t st, int keep0 = 0, int keep1 = -1, int post_reach = 0)
 {
+    // keep0/keep1/post_reach (row bands): only rows [keep0, keep1) of the result are used, after filters that reach
+    // post_reach rows.  Iteration k of K then only has to vote the rows within post_reach + usd * (K - 1 - k) of them:
+    // a vote further out cannot travel into the kept rows in the iterations that remain (each carries usd rows).
     const size_t n = (size_t)H * W;
     IrvArgs a;
     memset(&a, 0, sizeof(a));
@@ -1188,8 +1195,16 @@ static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2],
         if (dense_ok && iterations > 1 && iterations < 255) CU(cudaMemsetAsync(c->irv_stamp[v], 0, n, st));
     }
     if (iterations >= 255) for (int v = 0; v < nviews; ++v) a.stamp[v] = nullptr;
+    a.col_votes = dense_ok && !c->env_irv_list_votes && usd <= 64 ? c->env_irv_colw : 0;
     for (int it = 0; it < iterations; ++it) {
         a.it = it;
+        a.row_lo = 0;
+        a.row_hi = H;
+        if (keep1 >= 0) {
+            const int m = post_reach + usd * (iterations - 1 - it);
+            a.row_lo = std::max(0, keep0 - m);
+            a.row_hi = std::min(H, keep1 + m);
+        }
         if (dense_ok) {
             {
                 const dim3 gh(c->sm_count * 8, nviews);
@@ -1203,7 +1218,13 @@ static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2],
             }
             KCHECK();
             const dim3 gd(c->sm_count * 8, nviews);
-            switch (a.nbp / 128) {
+            if (a.col_votes) switch (a.nbp / 128) {
+                case 1: k_irv_vote_col<1><<<gd, kIrvWarps * 32, 0, st>>>(a); break;
+                case 2: k_irv_vote_col<2><<<gd, kIrvWarps * 32, 0, st>>>(a); break;
+                case 3: k_irv_vote_col<3><<<gd, kIrvWarps * 32, 0, st>>>(a); break;
+                default: k_irv_vote_col<4><<<gd, kIrvWarps * 32, 0, st>>>(a); break;
+            }
+            else switch (a.nbp / 128) {
                 case 1: k_irv_vote_dense<1><<<gd, kIrvWarps * 32, 0, st>>>(a); break;
                 case 2: k_irv_vote_dense<2><<<gd, kIrvWarps * 32, 0, st>>>(a); break;
                 case 3: k_irv_vote_dense<3><<<gd, kIrvWarps * 32, 0, st>>>(a); break;
@@ -1369,8 +1390,10 @@ static int run_refine(s2mv_ctx *c, float *fl, float *fr, cudaStream_t st)
         float *disp[2] = {c->disp[0], c->disp[1]};
         uint8_t *outl[2] = {c->outl[0], c->outl[1]};
         const uint32_t *arms[2] = {c->arms[0], c->arms[1]};
+        // a row band keeps its own rows only; what follows the voting reaches bilateral + bleed + mask blur rows
+        const int post = p.bilateral_radius + 1 + p.mask_blur_radius;
         TRY(launch_irv(c, disp, outl, arms, 2, H, W, p.num_disp, p.zero_disp, p.usd, p.thresh_s, p.thresh_h,
-                       p.irv_iterations, st));
+                       p.irv_iterations, st, c->band ? c->band_o0 : 0, c->band ? c->band_o1 : -1, post));
     }
     if (c->taps)
         for (int v = 0; v < 2; ++v)

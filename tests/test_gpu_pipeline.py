@@ -220,12 +220,14 @@ def test_frame_stream_matches_synchronous_call():
         assert np.array_equal(out, want[0][2])
 
 
-@pytest.mark.parametrize("dense_min", ["0", "2000000000"])
-def test_region_voting_dense_and_sparse_paths_agree_with_oracle(s2mv, oracle, bud_sbs, dense_min, monkeypatch):
-    # the two implementations of the vote (per-pixel span histograms summed per outlier / per-outlier gather)
-    # are forced in turn on the same frames: an outlier-heavy synthetic one and a bundled pair
+@pytest.mark.parametrize("dense_min,list_votes", [("0", "0"), ("0", "1"), ("2000000000", "0")])
+def test_region_voting_dense_and_sparse_paths_agree_with_oracle(s2mv, oracle, bud_sbs, dense_min, list_votes, monkeypatch):
+    # the three implementations of the vote (per-pixel span histograms summed along each column with a sliding row
+    # window / summed per outlier / per-outlier gather) are forced in turn on the same frames: an outlier-heavy
+    # synthetic one and a bundled pair
     from s2mv_b200_pkg import synth
     monkeypatch.setenv("S2MV_IRV_DENSE_MIN", dense_min)
+    monkeypatch.setenv("S2MV_IRV_LIST_VOTES", list_votes)
     with s2mv.Pipeline(0) as p:
         got, want = run_both(p, oracle, synth.make_sbs(120, 352, 77), 352, 48, 24)
         assert (want[3]["outliers_l"] != 0).mean() > 0.05
