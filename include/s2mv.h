@@ -153,10 +153,20 @@ int s2mv_synchronize(s2mv_ctx *ctx);
  *   fill the other rows of s2mv_band_disp() planes from the other bands
  *   s2mv_band_finish()                 refinement + DIBR + interlace, own rows out
  *
+ * s2mv_configure_band_ex additionally takes the row count of the frame's SMALLEST band and fuse_vertical (the
+ * same values on every band).  When every band has at least 2*usd rows (and num_disp > 64) the two vertical
+ * passes can run as one launch: the bands then exchange 2*usd rows of volume A once (s2mv_band_info reports
+ * the rows per exchange), s2mv_band_pass(2) does both vertical passes, s2mv_band_halo(2, ...) returns 0 bytes
+ * and s2mv_band_pass(3) returns at once -- the call sequence above stays valid as it is.  fuse_vertical: 0 = never,
+ * 1 = whenever possible, -1 = where it is faster (bands of 40*usd rows and more).  s2mv_configure_band = _ex
+ * with (0, 0).
+ *
  * Results equal the single-context frame bit for bit (tests/test_gpu_rowband.py).
  * All pointers are DEVICE pointers; every call is asynchronous on `stream`
  * (NULL = the context's stream).  Requires output size == input size. */
 int s2mv_configure_band(s2mv_ctx *ctx, const s2mv_params *frame, int band_y0, int band_y1, int apron);
+int s2mv_configure_band_ex(s2mv_ctx *ctx, const s2mv_params *frame, int band_y0, int band_y1, int apron, int min_band_rows,
+                           int fuse_vertical);
 int s2mv_band_info(const s2mv_ctx *ctx, int *local_y0, int *local_rows, int *own_first, int *own_rows, int *halo_rows);
 int s2mv_band_prepare(s2mv_ctx *ctx, const uint8_t *d_img_sbs_frame, int num_cols_sbs, void *stream);
 int s2mv_band_pass(s2mv_ctx *ctx, int pass, void *stream);
@@ -178,6 +188,7 @@ typedef struct {
     int frame_y0, frame_y1;     /* the band's own rows in the frame */
     int local_y0, vlo, vrows;   /* sub-image origin, first volume row (local), volume rows */
     int num_cols, lptot, frame_rows, device;
+    int halo_rows, fused;       /* rows of volume A exchanged per neighbour; vertical passes fused (must agree) */
 } s2mv_band_ipc;
 int s2mv_band_connect(s2mv_ctx *ctx, int side, s2mv_ctx *neighbour);
 int s2mv_band_ipc_export(s2mv_ctx *ctx, s2mv_band_ipc *out);

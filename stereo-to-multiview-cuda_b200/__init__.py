@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "s2mv_dibr_dbm", "s2mv_dibr_dfm", "s2mv_mux_multiview",
     "s2mv_stream_open", "s2mv_stream_input_buffer", "s2mv_stream_submit", "s2mv_stream_collect",
     "s2mv_stream_pending", "s2mv_stream_close", "s2mv_set_chunk_sequential", "s2mv_is_chunk_sequential",
-    "s2mv_configure_band", "s2mv_band_info", "s2mv_band_prepare", "s2mv_band_pass", "s2mv_band_halo",
+    "s2mv_configure_band", "s2mv_configure_band_ex", "s2mv_band_info", "s2mv_band_prepare", "s2mv_band_pass", "s2mv_band_halo",
     "s2mv_band_disp", "s2mv_band_finish", "s2mv_band_connect", "s2mv_band_ipc_export", "s2mv_band_ipc_connect",
     "s2mv_band_status", "s2mv_dc_so", "s2mv_enable_so",
     "s2mv_configure_2", "s2mv_process_sbs_2", "s2mv_process_sbs_2_device", "s2mv_set_host_registration",

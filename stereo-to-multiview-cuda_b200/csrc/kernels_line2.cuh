@@ -670,7 +670,19 @@ struct LineVVArgs {
     int tiles_per_col, ncols, nz, nclaims;
     int *counter;
     int tmap_rows;        // rows per tensor copy (the map's box): a tile is P / tmap_rows copies
+    // Rows stored, [out_r0, out_r1): all a.H rows of a whole image.  A row band runs the kernel over the rows its buffer A
+    // holds (its own rows and 2*usd rows of each neighbour) as if they were an image: arms are cut at the first and last
+    // of them, which changes V2 only within usd rows of those edges and V3 only within 2*usd -- outside the own rows
+    // [out_r0, out_r1), the only ones stored.
+    int out_r0, out_r1;
 };
+
+// arm word of row r of an H-row column with the vertical arms cut at rows 0 and H-1 (whole images: already are)
+__device__ __forceinline__ uint32_t arm_cut_v(uint32_t w, int r, int H)
+{
+    const uint32_t up = min(w & 0xffu, (uint32_t)r), dn = min((w >> 8) & 0xffu, (uint32_t)(H - 1 - r));
+    return (w & 0xffff0000u) | (dn << 8) | up;
+}
 
 struct LineVVDesc {
     int valid, col, vslot, chunk, j, colbase, pad0, pad1;
@@ -798,7 +810,7 @@ k_line_vv(const __grid_constant__ LineVVArgs L, const __grid_constant__ CUtensor
                 for (int k = 0; k < B; ++k) {
                     const int r = g * B + k;
                     nxt[k] = 0u;
-                    if (i >= 0 && r < H) nxt[k] = __ldg(a.arms[vslot] + (size_t)r * W + col);
+                    if (i >= 0 && r < H) nxt[k] = arm_cut_v(__ldg(a.arms[vslot] + (size_t)r * W + col), r, H);
                 }
             }
             if (pend_bar) {
@@ -853,6 +865,7 @@ k_line_vv(const __grid_constant__ LineVVArgs L, const __grid_constant__ CUtensor
                 const int g = i < NBS ? NBH + d.j * NBS + i : i - NBS;
                 const int slot = (d.colbase + g) % kVVMaskRing;
                 const int r0 = g * B;                       // first row of the block
+                if (r0 + B <= L.out_r0 - HP || r0 >= L.out_r1 + HP) continue;  // no stored row reads this block
                 // frame position 0 = row r0 - HP = H1 tile position r0 - HP - jS
                 float4 acc[B];
                 sum_block_masked<B>(h1, smem_u32(sMask + (size_t)slot * FR), sBounds[slot], r0 - HP - d.j * S, acc);
@@ -881,7 +894,8 @@ k_line_vv(const __grid_constant__ LineVVArgs L, const __grid_constant__ CUtensor
             char *colp = reinterpret_cast<char *>(a.out[d.vslot] + (size_t)d.col * a.LPtot + (size_t)d.chunk * 32 + lane);
             for (int i = w; i < NBS; i += NA) {
                 const int g = d.j * NBS + i, r0 = g * B;
-                if (r0 >= H) break;
+                if (r0 >= L.out_r1) break;
+                if (r0 + B <= L.out_r0) continue;
                 const int slot = (d.colbase + g) % kVVMaskRing;
                 // frame position 0 = row r0 - HP = V2 buffer position r0 - jS
                 float4 acc[B];
@@ -889,7 +903,7 @@ k_line_vv(const __grid_constant__ LineVVArgs L, const __grid_constant__ CUtensor
                 char *dstp = colp + (long long)r0 * ostride;
 #pragma unroll
                 for (int k = 0; k < B; ++k)
-                    if (r0 + k < H) *reinterpret_cast<float4 *>(dstp + k * ostride) = acc[k];
+                    if (r0 + k >= L.out_r0 && r0 + k < L.out_r1) *reinterpret_cast<float4 *>(dstp + k * ostride) = acc[k];
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(v3done(vb));

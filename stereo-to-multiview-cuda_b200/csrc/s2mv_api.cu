@@ -274,6 +274,8 @@ struct s2mv_ctx {
     // row-band mode (s2mv_band.inl): this context is a sub-image of a taller frame
     bool band = false;
     int band_frame_rows = 0, band_ly0 = 0, band_o0 = 0, band_o1 = 0, band_vlo = 0, band_vhi = 0;
+    int band_halo1 = 0;        // rows of pass 1's output exchanged with each neighbour: usd, or 2*usd when band_fused
+    bool band_fused = false;   // the two vertical passes run as one launch (k_line_vv) on the band's rows
     // peer-to-peer halos: the neighbours' volumes as seen from this process / device
     struct BandPeer {
         bool connected = false;
@@ -593,7 +595,7 @@ static int build_luts(s2mv_ctx *c, float ad_coeff, float census_coeff, cudaStrea
     return S2MV_OK;
 }
 
-struct BandSpec { int frame_rows, ly0, o0, o1, vlo, vhi; };
+struct BandSpec { int frame_rows, ly0, o0, o1, sub_rows, min_band_rows, fuse; };
 static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *band);
 
 extern "C" int s2mv_configure(s2mv_ctx *c, const s2mv_params *p)
@@ -695,7 +697,20 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
     if (c->so_on && (pl.nchunks != 1 || band)) c->so_on = false;  // only for num_disp <= 128, whole frames
     if (band) {
         c->band_frame_rows = band->frame_rows; c->band_ly0 = band->ly0; c->band_o0 = band->o0; c->band_o1 = band->o1;
-        c->band_vlo = band->vlo; c->band_vhi = band->vhi;
+        // The vertical passes read usd rows beyond the rows they write.  Run one after the other, the band receives usd
+        // rows of pass 1's output and then usd rows of pass 2's from each neighbour.  Fused (k_line_vv), it receives
+        // 2*usd rows of pass 1's output once and forms the usd rows of pass 2's output next to its edges itself; the
+        // neighbours must own that many rows, which the caller states (min_band_rows: every band of the frame must
+        // reach the same decision).  Fusing pays when the 4*usd extra rows per band (pass 1 stores them twice, the fused
+        // kernel walks them) are a small part of it: measured on 4K D=256, 1080-row bands gain 2 %, 540-row bands lose
+        // 3 %, 270-row bands lose 3 % (profiles/r2_experiments.md); fuse < 0 takes bands of 40*usd rows and more.
+        const bool can_fuse = pl.vv && encode_tiled_fn() != nullptr && !c->env_no_vv && !c->env_line_v1 && !c->env_line_bulk &&
+                              band->min_band_rows >= 2 * p->usd;
+        const bool fused = can_fuse && (band->fuse > 0 || (band->fuse < 0 && band->min_band_rows >= 40 * p->usd));
+        c->band_fused = fused;
+        c->band_halo1 = fused ? 2 * p->usd : p->usd;
+        c->band_vlo = std::max(0, band->o0 - c->band_halo1);
+        c->band_vhi = std::min(band->sub_rows, band->o1 + c->band_halo1);
     }
     c->lut_ad_coeff = c->lut_cen_coeff = -1.f;
     const size_t n = (size_t)p->num_rows * p->num_cols;
@@ -714,7 +729,7 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
         }
     }
     // a row band keeps only its own rows plus usd halo rows either side of the volumes
-    const size_t vol_rows = band ? (size_t)(band->vhi - band->vlo) : (size_t)p->num_rows;
+    const size_t vol_rows = band ? (size_t)(c->band_vhi - c->band_vlo) : (size_t)p->num_rows;
     const size_t vol_elems = c->no_volume ? 4 : 2 * vol_rows * p->num_cols * (pl.chunk_seq ? 4 * pl.LP : pl.Dp);
     for (int v = 0; v < 2; ++v) {
         TRY(dev_alloc_t(c, &c->pix[v], n));
@@ -789,6 +804,7 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
     TRY(build_luts(c, p->ad_coeff, p->census_coeff, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->tmap_ok = make_volume_tmaps(c, vol_rows);
+    if (band && !c->tmap_ok) c->band_fused = false;  // the wider halo stays: the separate passes only use usd rows of it
     c->configured = true;
     return S2MV_OK;
 }
@@ -1032,12 +1048,19 @@ static int launch_aggregate(s2mv_ctx *c, const LineArgs &a, float4 *A, float4 *B
 
 // The two vertical passes in one launch (k_line_vv): reads volume buffer A (pass 1's output) through its tensor map,
 // writes buffer B.  Whole-frame contexts only (a row band exchanges pass 2's output with its neighbours).
-static int launch_vv(s2mv_ctx *c, LineArgs a, float4 *Bout, size_t view_stride4, int nviews, cudaStream_t st)
+// rows: the rows buffer A holds, as image rows [vlo, vhi) of `a`, and the rows [own0, own1) to store (a whole image: 0, H, 0, H).
+static int launch_vv(s2mv_ctx *c, LineArgs a, float4 *Bout, size_t view_stride4, int nviews, const RowRange &rr, cudaStream_t st)
 {
     const CostPlan &pl = c->plan;
     LineVVArgs L;
     memset(&L, 0, sizeof(L));
-    for (int v = 0; v < nviews; ++v) a.out[v] = Bout + v * view_stride4;
+    for (int v = 0; v < nviews; ++v) {
+        a.out[v] = Bout + v * view_stride4;                 // row 0 of the launch = image row vlo = the buffers' first row
+        a.arms[v] += (size_t)rr.vlo * a.W;
+    }
+    a.H = rr.vhi - rr.vlo;
+    L.out_r0 = rr.own0 - rr.vlo;
+    L.out_r1 = rr.own1 - rr.vlo;
     L.a = a;
     L.S = pl.vv_S; L.HP = pl.vv_HP; L.P = L.S + 2 * L.HP;
     L.tiles_per_col = (a.H + L.S - 1) / L.S;
@@ -1115,7 +1138,7 @@ static int launch_costvol(s2mv_ctx *c, float *dispL, float *dispR, cudaStream_t 
         if (c->timing) CU(cudaEventRecord(c->kev[0], st));
         TRY(launch_pass(c, aa, 1, A, B, view_stride4, 2, true, true, rr, st));
         if (c->timing) CU(cudaEventRecord(c->kev[1], st));
-        TRY(launch_vv(c, aa, B, view_stride4, 2, st));
+        TRY(launch_vv(c, aa, B, view_stride4, 2, rr, st));
         if (c->timing) { CU(cudaEventRecord(c->kev[2], st)); CU(cudaEventRecord(c->kev[3], st)); }
         TRY(launch_pass(c, aa, 4, /*read*/ B, /*unused*/ A, view_stride4, 2, true, true, rr, st));
         if (c->timing) CU(cudaEventRecord(c->kev[4], st));

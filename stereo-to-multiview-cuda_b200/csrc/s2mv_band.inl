@@ -30,7 +30,8 @@ static int band_poisoned(const s2mv_ctx *c)
     return S2MV_OK;
 }
 
-extern "C" int s2mv_configure_band(s2mv_ctx *c, const s2mv_params *frame, int band_y0, int band_y1, int apron)
+static int configure_band_impl(s2mv_ctx *c, const s2mv_params *frame, int band_y0, int band_y1, int apron, int min_band_rows,
+                               int fuse)
 {
     if (!c || !frame) return fail(S2MV_ERR_BAD_PARAM, "null argument");
     const int H = frame->num_rows, usd = frame->usd;
@@ -48,11 +49,29 @@ extern "C" int s2mv_configure_band(s2mv_ctx *c, const s2mv_params *frame, int ba
     const int ly1 = band_y1 + apron < H ? band_y1 + apron : H;
     b.o0 = band_y0 - b.ly0;
     b.o1 = band_y1 - b.ly0;
-    b.vlo = b.o0 - usd > 0 ? b.o0 - usd : 0;
-    b.vhi = b.o1 + usd < ly1 - b.ly0 ? b.o1 + usd : ly1 - b.ly0;
+    b.sub_rows = ly1 - b.ly0;
+    b.min_band_rows = min_band_rows;
+    b.fuse = fuse;
     s2mv_params p = *frame;
     p.num_rows = p.num_rows_out = ly1 - b.ly0;
-    return configure_impl(c, &p, &b);
+    return configure_impl(c, &p, &b);   // the volume rows [vlo, vhi) follow from the plan (fused vertical passes or not)
+}
+
+extern "C" int s2mv_configure_band(s2mv_ctx *c, const s2mv_params *frame, int band_y0, int band_y1, int apron)
+{
+    return configure_band_impl(c, frame, band_y0, band_y1, apron, 0, 0);
+}
+
+// min_band_rows: the smallest band of the frame; fuse_vertical: 0 = two vertical passes, 1 = one launch whenever every band
+// has 2*usd rows, -1 = one launch where that is faster (tall bands).  The same values on every band of the frame.  Fused,
+// the bands exchange halo rows once, not twice (s2mv_band_info reports the rows per exchange; pass 3 is then part of
+// pass 2 and returns at once).
+extern "C" int s2mv_configure_band_ex(s2mv_ctx *c, const s2mv_params *frame, int band_y0, int band_y1, int apron,
+                                      int min_band_rows, int fuse_vertical)
+{
+    if (frame && min_band_rows > 0 && band_y1 - band_y0 < min_band_rows)
+        return fail(S2MV_ERR_BAD_PARAM, "band of %d rows is smaller than min_band_rows %d", band_y1 - band_y0, min_band_rows);
+    return configure_band_impl(c, frame, band_y0, band_y1, apron, min_band_rows, fuse_vertical);
 }
 
 extern "C" int s2mv_band_info(const s2mv_ctx *c, int *local_y0, int *local_rows, int *own_first, int *own_rows,
@@ -63,7 +82,7 @@ extern "C" int s2mv_band_info(const s2mv_ctx *c, int *local_y0, int *local_rows,
     if (local_rows) *local_rows = c->prm.num_rows;
     if (own_first) *own_first = c->band_o0;
     if (own_rows) *own_rows = c->band_o1 - c->band_o0;
-    if (halo_rows) *halo_rows = c->prm.usd;
+    if (halo_rows) *halo_rows = c->band_halo1;
     return S2MV_OK;
 }
 
@@ -114,9 +133,12 @@ extern "C" int s2mv_band_pass(s2mv_ctx *c, int pass, void *stream)
     fill_largs(c, a, p.num_rows, p.num_cols, p.zero_disp, p.ad_coeff);
     for (int v = 0; v < 2; ++v) { a.arms[v] = c->arms[v]; a.wta_key[v] = c->wta_key[v]; a.disp[v] = c->disp[v]; }
     const bool p2p = c->band_peer[0].connected || c->band_peer[1].connected;
+    const bool fused = c->band_fused;
+    if (fused && pass == 3) return S2MV_OK;                        // done by pass 2
+    const bool waits = pass == 2 || (pass == 3 && !fused), pushes = pass == 1 || (pass == 2 && !fused);
     a.peer_lo_end = 0;
     a.peer_hi_begin = 0x7fffffff;
-    if (p2p && (pass == 2 || pass == 3)) {
+    if (p2p && waits) {
         // the halo rows this pass reads are written by the neighbours' previous pass: wait for their epoch
         for (int side = 0; side < 2; ++side)
             if (c->band_peer[side].connected) {
@@ -124,9 +146,9 @@ extern "C" int s2mv_band_pass(s2mv_ctx *c, int pass, void *stream)
                 KCHECK();
             }
     }
-    if (p2p && (pass == 1 || pass == 2)) {
+    if (p2p && pushes) {
         // this pass's rows next to a band edge also go straight into the neighbour's halo rows
-        const int usd = p.usd, buf = pass == 1 ? 0 : 1;
+        const int usd = pass == 1 ? c->band_halo1 : p.usd, buf = pass == 1 ? 0 : 1;
         for (int side = 0; side < 2; ++side) {
             const s2mv_ctx::BandPeer &pr = c->band_peer[side];
             if (!pr.connected) continue;
@@ -136,9 +158,15 @@ extern "C" int s2mv_band_pass(s2mv_ctx *c, int pass, void *stream)
             if (side == 0) a.peer_lo_end = rr.own0 + usd; else a.peer_hi_begin = rr.own1 - usd;
         }
     }
-    TRY(launch_pass(c, a, pass, reinterpret_cast<float4 *>(c->vol[0]), reinterpret_cast<float4 *>(c->vol[1]), view_stride4,
-                    2, true, true, rr, st));
-    if (p2p && (pass == 1 || pass == 2)) {
+    float4 *A = reinterpret_cast<float4 *>(c->vol[0]), *B = reinterpret_cast<float4 *>(c->vol[1]);
+    if (fused && pass == 2) {
+        TRY(launch_vv(c, a, B, view_stride4, 2, rr, st));          // A (own rows + 2*usd halo rows) -> B (own rows)
+    } else if (fused && pass == 4) {
+        TRY(launch_pass(c, a, 4, /*read*/ B, /*unused*/ A, view_stride4, 2, true, true, rr, st));
+    } else {
+        TRY(launch_pass(c, a, pass, A, B, view_stride4, 2, true, true, rr, st));
+    }
+    if (p2p && pushes) {
         c->band_epoch += 1;
         for (int side = 0; side < 2; ++side)
             if (c->band_peer[side].connected) {
@@ -167,7 +195,7 @@ extern "C" int s2mv_band_halo(s2mv_ctx *c, int after_pass, int view, int side, i
     RowRange rr;
     size_t row4, view_stride4;
     band_geometry(c, rr, row4, view_stride4);
-    const int usd = c->prm.usd;
+    const int usd = after_pass == 1 ? c->band_halo1 : (c->band_fused ? 0 : c->prm.usd);
     const bool at_edge = side == 0 ? (c->band_ly0 + rr.own0 == 0) : (c->band_ly0 + rr.own1 == c->band_frame_rows);
     int r0, r1;
     if (side == 0) { r0 = recv ? rr.own0 - usd : rr.own0; r1 = r0 + usd; }
@@ -239,6 +267,8 @@ extern "C" int s2mv_band_connect(s2mv_ctx *c, int side, s2mv_ctx *peer)
     const int my_edge = c->band_ly0 + (side == 0 ? c->band_o0 : c->band_o1);
     const int peer_edge = peer->band_ly0 + (side == 0 ? peer->band_o1 : peer->band_o0);
     if (my_edge != peer_edge) return fail(S2MV_ERR_BAD_PARAM, "bands are not adjacent (rows %d vs %d)", my_edge, peer_edge);
+    if (peer->band_halo1 != c->band_halo1 || peer->band_fused != c->band_fused)
+        return fail(S2MV_ERR_BAD_PARAM, "neighbour bands were configured with different halo exchanges (min_band_rows must agree)");
     if (peer->device != c->device) {
         CU(cudaSetDevice(c->device));
         cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
@@ -280,6 +310,8 @@ extern "C" int s2mv_band_ipc_export(s2mv_ctx *c, s2mv_band_ipc *out)
     out->lptot = c->plan.LPtot;
     out->frame_rows = c->band_frame_rows;
     out->device = c->device;
+    out->halo_rows = c->band_halo1;
+    out->fused = c->band_fused ? 1 : 0;
     return S2MV_OK;
 }
 
@@ -292,6 +324,8 @@ extern "C" int s2mv_band_ipc_connect(s2mv_ctx *c, int side, const s2mv_band_ipc 
     const int my_edge = c->band_ly0 + (side == 0 ? c->band_o0 : c->band_o1);
     const int peer_edge = side == 0 ? peer->frame_y1 : peer->frame_y0;
     if (my_edge != peer_edge) return fail(S2MV_ERR_BAD_PARAM, "bands are not adjacent (rows %d vs %d)", my_edge, peer_edge);
+    if (peer->halo_rows != c->band_halo1 || (peer->fused != 0) != c->band_fused)
+        return fail(S2MV_ERR_BAD_PARAM, "neighbour bands were configured with different halo exchanges (min_band_rows must agree)");
     CU(cudaSetDevice(c->device));
     s2mv_ctx::BandPeer &pr = c->band_peer[side];
     void *m[3] = {};

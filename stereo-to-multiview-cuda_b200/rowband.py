@@ -75,20 +75,24 @@ class BandIpc(C.Structure):
     """s2mv_band_ipc (include/s2mv.h): what a neighbouring process needs to map a band's volumes."""
     _fields_ = [("mem", (C.c_ubyte * 64) * 3), ("frame_y0", C.c_int), ("frame_y1", C.c_int), ("local_y0", C.c_int),
                 ("vlo", C.c_int), ("vrows", C.c_int), ("num_cols", C.c_int), ("lptot", C.c_int), ("frame_rows", C.c_int),
-                ("device", C.c_int)]
+                ("device", C.c_int), ("halo_rows", C.c_int), ("fused", C.c_int)]
 
 
 class RowBand:
     """One band context: thin mirror of the s2mv_band_* C ABI with torch views of its halo runs."""
 
-    def __init__(self, device, band_y0, band_y1, apron=0, **frame_params):
+    def __init__(self, device, band_y0, band_y1, apron=0, min_band_rows=0, fuse_vertical=None, **frame_params):
+        """min_band_rows: rows of the frame's smallest band (0 = unknown: separate vertical passes, usd halo rows);
+        fuse_vertical: True = one launch for both vertical passes whenever every band has 2*usd rows, False = never,
+        None = where it is faster (tall bands)."""
         from . import Pipeline, default_params, lib
         _declare(lib())
         self.pipe = Pipeline(device)
         self.device = device
         L = self.pipe._L
         p = default_params(**frame_params)
-        _check(L.s2mv_configure_band(self.pipe._ctx, C.byref(p), int(band_y0), int(band_y1), int(apron)))
+        _check(L.s2mv_configure_band_ex(self.pipe._ctx, C.byref(p), int(band_y0), int(band_y1), int(apron),
+                                        int(min_band_rows), -1 if fuse_vertical is None else int(bool(fuse_vertical))))
         self.frame = p
         self.y0, self.y1 = band_y0, band_y1
         v = [C.c_int() for _ in range(5)]
@@ -160,6 +164,7 @@ def _declare(L):
     L.s2mv_band_disp.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.s2mv_band_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.s2mv_configure_band.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.s2mv_configure_band_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.s2mv_band_info.argtypes = [C.c_void_p] + [C.c_void_p] * 5
     L.s2mv_band_connect.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.s2mv_band_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
@@ -172,7 +177,7 @@ class LocalBands:
     """All bands of a frame in this process; `devices` gives each band's GPU (repeat an index to run
     several bands on one GPU).  process() returns the assembled (disp_l, disp_r, interlaced) tensors."""
 
-    def __init__(self, devices, apron=0, p2p=True, **frame_params):
+    def __init__(self, devices, apron=0, p2p=True, fuse_vertical=None, **frame_params):
         """p2p: the producing passes store the halo rows straight into the neighbouring band's volume (peer stores,
         epoch words on the stream); False: halos are copied between the passes (Tensor.copy_)."""
         import torch
@@ -181,7 +186,8 @@ class LocalBands:
         p = default_params(**frame_params)
         self.H, self.W = p.num_rows, p.num_cols
         self.bands = row_bands(self.H, len(devices), min_rows=p.usd)
-        self.ctx = [RowBand(d, y0, y1, apron, **frame_params) for d, (y0, y1) in zip(devices, self.bands)]
+        mbr = min(y1 - y0 for y0, y1 in self.bands)
+        self.ctx = [RowBand(d, y0, y1, apron, mbr, fuse_vertical, **frame_params) for d, (y0, y1) in zip(devices, self.bands)]
         self.p2p = p2p
         if p2p:
             for b, c in enumerate(self.ctx):
@@ -205,7 +211,8 @@ class LocalBands:
                 for view in (0, 1):
                     src = c.halo(after_pass, view, send_side, False)
                     dst = self.ctx[peer].halo(after_pass, view, 1 - send_side, True)
-                    dst.copy_(src)
+                    if src is not None and dst is not None:   # nothing after pass 2 when the vertical passes are fused
+                        dst.copy_(src)
         self._sync()
 
     def process(self, d_sbs_by_device, num_cols_sbs):
@@ -294,7 +301,7 @@ def allgather_rows_dist(own, bands, dist, torch):
 class DistBand:
     """This rank's band of a frame split over the process group (one process per GPU)."""
 
-    def __init__(self, device, rank, world, apron=0, transport="p2p", **frame_params):
+    def __init__(self, device, rank, world, apron=0, transport="p2p", fuse_vertical=None, **frame_params):
         """transport "p2p": neighbours' volumes mapped through CUDA IPC, halo rows stored over NVLink by the
         producing kernels; "nccl": halos sent with torch.distributed point-to-point ops between the passes."""
         import torch
@@ -307,7 +314,8 @@ class DistBand:
         self.rank, self.world = rank, world
         self.bands = row_bands(self.H, world, min_rows=p.usd)
         y0, y1 = self.bands[rank]
-        self.ctx = RowBand(device, y0, y1, apron, **frame_params)
+        mbr = min(b1 - b0 for b0, b1 in self.bands)
+        self.ctx = RowBand(device, y0, y1, apron, mbr, fuse_vertical, **frame_params)
         c = self.ctx
         self.out_l = torch.empty((c.own_rows, self.W), dtype=torch.float32, device=f"cuda:{device}")
         self.out_r = torch.empty_like(self.out_l)

@@ -12,9 +12,14 @@ ALGO = {k: DEFAULTS[k] for k in ("ad_coeff", "census_coeff", "ucd", "lcd", "usd"
 
 
 @pytest.mark.parametrize("p2p", [True, False])
-@pytest.mark.parametrize("H,W,D,zd,nbands", [(400, 320, 32, 16, 3), (300, 336, 160, 70, 2), (531, 200, 64, 32, 4),
-                                             (120, 192, 128, 60, 5)])
-def test_row_bands_equal_whole_frame(s2mv, H, W, D, zd, nbands, p2p):
+@pytest.mark.parametrize("H,W,D,zd,nbands,fuse", [
+    (400, 320, 32, 16, 3, None), (300, 336, 160, 70, 2, None), (531, 200, 64, 32, 4, True), (120, 192, 128, 60, 5, True),
+    # bands of >= 2*usd rows with num_disp > 64: the vertical passes run fused, one exchange of 2*usd rows;
+    # 40-row bands send the same rows to both neighbours; then the passes kept separate on such a frame, and the
+    # library's own choice (None: fused from 40*usd rows per band)
+    (300, 336, 128, 60, 3, True), (300, 336, 160, 70, 2, True), (200, 256, 96, 40, 5, True), (300, 336, 128, 60, 3, False),
+    (1400, 96, 72, 30, 2, None)])
+def test_row_bands_equal_whole_frame(s2mv, H, W, D, zd, nbands, fuse, p2p):
     import torch
     from s2mv_b200_pkg import rowband, synth
     sbs = synth.make_sbs(H, W, 4000 + H)
@@ -23,9 +28,12 @@ def test_row_bands_equal_whole_frame(s2mv, H, W, D, zd, nbands, p2p):
         wl, wr, wo = p.adcensus_stm(sbs)
     # p2p: halo rows stored by the producing pass straight into the neighbouring band's volume (here: another
     # context on the same GPU), epoch words on the stream; otherwise copied between the passes
-    lb = rowband.LocalBands([0] * nbands, p2p=p2p, **params)
+    lb = rowband.LocalBands([0] * nbands, p2p=p2p, fuse_vertical=fuse, **params)
     try:
         assert [c.own_rows for c in lb.ctx] == [y1 - y0 for y0, y1 in lb.bands]
+        rows = min(c.own_rows for c in lb.ctx)
+        fused = D > 64 and ((fuse and rows >= 2 * ALGO["usd"]) or (fuse is None and rows >= 40 * ALGO["usd"]))
+        assert all(c.halo_rows == (2 if fused else 1) * ALGO["usd"] for c in lb.ctx)
         d_sbs = torch.from_numpy(sbs).cuda()
         dl, dr, out = lb.process({0: d_sbs}, 2 * W)
         assert np.array_equal(dl.cpu().numpy(), wl)

@@ -38,6 +38,9 @@ def main():
     ap.add_argument("--baseline", action="store_true", help="also time the single-context frame on rank 0")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
                     help="halo rows: peer stores from the producing kernels over CUDA IPC mappings, or NCCL send/recv")
+    ap.add_argument("--vertical", default="auto", choices=["auto", "fused", "separate"],
+                    help="the two vertical passes: one launch per band with one exchange of 2*usd rows (needs bands of 2*usd "
+                         "rows), two launches with two exchanges of usd rows, or the library's choice (fused for tall bands)")
     ap.add_argument("--sha", action="store_true", help="print SHA-256 of the assembled outputs (to compare runs whose "
                                                        "single-context frame does not fit next to a band)")
     ap.add_argument("--single", action="store_true", help="N = 1 only: time the ordinary single-context frame "
@@ -87,7 +90,9 @@ def measure(args):
                            (("disp_l", d_dl), ("disp_r", d_dr), ("interlaced", d_out))}}
         return res
 
-    band = rowband.DistBand(local_rank, rank, world, transport=args.transport, **params)
+    band = rowband.DistBand(local_rank, rank, world, transport=args.transport,
+                            fuse_vertical={"auto": None, "fused": True, "separate": False}[getattr(args, "vertical", "auto")],
+                            **params)
     for _ in range(args.warmup):
         band.process(d_sbs, 2 * W)
     torch.cuda.synchronize()
@@ -116,7 +121,7 @@ def measure(args):
                        "full pipeline (disparities + 8-view interlaced frame)",
            "n_gpus": world, "ms_per_frame": ms, "frames_per_s": 1e3 / ms, "steps": args.steps,
            "band_rows": [y1 - y0 for y0, y1 in band.bands], "sub_image_rows": band.ctx.local_rows,
-           "halo_rows": band.ctx.halo_rows, "halo_bytes_per_exchange_per_neighbour": 2 * band.ctx.halo_rows * W * 4 * (
+           "halo_rows": band.ctx.halo_rows, "vertical_passes": "fused" if band.ctx.halo_rows > params["usd"] else "separate", "halo_bytes_per_exchange_per_neighbour": 2 * band.ctx.halo_rows * W * 4 * (
                (D + 127) // 128 * 128 if D > 128 else 1 << (max(D, 4) - 1).bit_length()),
            "phase_ms_max_over_ranks": {k: max(p[k] for p in allph) for k in phases},
            "phase_ms_rank0": phases,
