@@ -286,6 +286,37 @@ def exchange_halos_dist(send_recv, rank, world, dist):
             w.wait()
 
 
+def disparity_row_plan(bands, extents, rank):
+    """Which disparity rows rank `rank` sends to and receives from which rank so that every sub-image
+    (extents[b] = (local_y0, local_rows) of band b) holds the WTA disparities of all its rows: two lists of
+    (peer, frame_y0, frame_y1), each ordered by peer and row (both ends of a pair post their ops in the same order)."""
+    send, recv = [], []
+    for b, (ly0, rows) in enumerate(extents):
+        for src, a, e in gather_rows(bands, ly0, rows):
+            if src == b:
+                continue
+            if src == rank:
+                send.append((b, a, e))
+            if b == rank:
+                recv.append((src, a, e))
+    return sorted(send), sorted(recv)
+
+
+def exchange_disparity_rows_dist(planes, local_y0, own_y0, send, recv, dist):
+    """planes: this band's sub-image disparity planes (one per view).  Own rows go out to the sub-images that
+    hold them in their aprons, the apron rows come in -- one batch of point-to-point ops (a band's apron reaches
+    its nearest neighbours only, unless bands are shorter than the apron; the plan covers both)."""
+    ops = []
+    for plane in planes:
+        for peer, a, e in send:
+            ops.append(dist.P2POp(dist.isend, plane[a - local_y0:e - local_y0], peer))
+        for peer, a, e in recv:
+            ops.append(dist.P2POp(dist.irecv, plane[a - local_y0:e - local_y0], peer))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
 def allgather_rows_dist(own, bands, dist, torch):
     """own: this rank's (own_rows x W) tensor.  Returns the (H x W) frame assembled from every rank's own rows
     (bands may differ by one row: planes are padded to the tallest band for the collective)."""
@@ -320,6 +351,10 @@ class DistBand:
         self.out_l = torch.empty((c.own_rows, self.W), dtype=torch.float32, device=f"cuda:{device}")
         self.out_r = torch.empty_like(self.out_l)
         self.out_i = torch.empty((c.own_rows, self.W, 3), dtype=torch.uint8, device=f"cuda:{device}")
+        if world > 1:
+            extents = [None] * world
+            dist.all_gather_object(extents, (c.local_y0, c.local_rows))
+            self._disp_send, self._disp_recv = disparity_row_plan(self.bands, extents, rank)
         if self.transport == "p2p":
             blobs = [None] * world
             dist.all_gather_object(blobs, c.ipc_export())
@@ -370,10 +405,9 @@ class DistBand:
         c.run_pass(4, st)
         mark("pass3+4")
         if self.world > 1:
-            for v in (0, 1):
-                plane = c.disp_plane(v)
-                frame = allgather_rows_dist(plane[c.own_first:c.own_first + c.own_rows], self.bands, dist, torch)
-                plane.copy_(frame[c.local_y0:c.local_y0 + c.local_rows])
+            # the apron rows of the WTA disparity planes come from the bands that own them (NCCL send/recv)
+            exchange_disparity_rows_dist([c.disp_plane(v) for v in (0, 1)], c.local_y0, c.y0, self._disp_send,
+                                         self._disp_recv, dist)
         mark("gather")
         c.finish(self.out_l, self.out_r, self.out_i, st)
         mark("finish")

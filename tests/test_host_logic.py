@@ -8,6 +8,7 @@ import sys
 import textwrap
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -108,10 +109,12 @@ def test_row_band_partition_and_schedules(s2mv):
         row_bands(30, 2, min_rows=17)
 
 
-def test_two_rank_gloo_halo_exchange_and_row_gather(s2mv, tmp_path):
-    """The distributed transport of the row-band mode on CPU tensors over gloo (world_size 2): after the
-    exchange each rank's halo rows hold the neighbour's edge rows, and the row all-gather rebuilds the frame
-    from uneven bands."""
+@pytest.mark.parametrize("WORLD", [2, 3])
+def test_gloo_halo_exchange_and_row_gather(s2mv, tmp_path, WORLD):
+    """The distributed transport of the row-band mode on CPU tensors over gloo (world_size 2 and 3): after the
+    exchange each rank's halo rows hold the neighbour's edge rows, the row all-gather rebuilds the frame from
+    uneven bands, and the disparity-row exchange fills every sub-image's apron (from beyond the nearest
+    neighbour too at world_size 3)."""
     script = tmp_path / "worker.py"
     script.write_text(textwrap.dedent(f"""
         import sys
@@ -143,12 +146,24 @@ def test_two_rank_gloo_halo_exchange_and_row_gather(s2mv, tmp_path):
             assert torch.equal(vol[v], frame[vlo:vhi] + 1000 * v), (rank, v)
         full = rowband.allgather_rows_dist(frame[y0:y1].clone(), bands, dist, torch)
         assert torch.equal(full, frame)
+        # disparity rows: every sub-image (own rows + an apron that spans MORE than the neighbouring band here)
+        # receives exactly the rows it does not own from the ranks that own them
+        apron = 17
+        ext = [(max(0, a - apron), min(H, b + apron) - max(0, a - apron)) for a, b in bands]
+        send, recv = rowband.disparity_row_plan(bands, ext, rank)
+        ly0, rows = ext[rank]
+        planes = [torch.full((rows, W), -1.0) for _ in range(2)]
+        for v in range(2):
+            planes[v][y0 - ly0:y1 - ly0] = frame[y0:y1] + 1000 * v
+        rowband.exchange_disparity_rows_dist(planes, ly0, y0, send, recv, dist)
+        for v in range(2):
+            assert torch.equal(planes[v], frame[ly0:ly0 + rows] + 1000 * v), (rank, v)
         print("RESULT ok", rank)
     """))
     port = _free_port()
     procs = []
-    for rank in range(2):
-        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+    for rank in range(WORLD):
+        env = dict(os.environ, RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(WORLD), MASTER_ADDR="127.0.0.1",
                    MASTER_PORT=str(port))
         procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
                                       stderr=subprocess.PIPE, text=True))

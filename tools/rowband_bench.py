@@ -126,8 +126,8 @@ def measure(args):
            "phase_ms_max_over_ranks": {k: max(p[k] for p in allph) for k in phases},
            "phase_ms_rank0": phases,
            "arena_gb_per_gpu": arena / 1e9, "transport": {"p2p": "halo rows stored by the producing kernels into CUDA-IPC-mapped neighbour volumes (NVLink), epoch words "
-                                "on the stream; NCCL all_gather of the disparity rows",
-                         "nccl": "torch.distributed NCCL send/recv of the halo rows + all_gather of the disparity rows",
+                                "on the stream; NCCL send/recv of the disparity rows each sub-image takes from other bands",
+                         "nccl": "torch.distributed NCCL send/recv of the halo rows and of the disparity rows each sub-image takes from other bands",
                          "none": "one band"}[band.transport]}
 
     if args.sha:
