@@ -751,7 +751,7 @@ k_line_vv(const __grid_constant__ LineVVArgs L, const __grid_constant__ CUtensor
         const int pw = warp - 2 * NA;
         int j = 0, jend = 0, col = 0, vslot = 0, chunk = 0, nclaim = 0, colbase = 0, nextbase = 0;
         uint32_t cur[B], pend_bar = 0;
-        int pend_slot = -1;
+        int pend_slot = -1, pend_r0 = 0;
 #pragma unroll
         for (int k = 0; k < B; ++k) cur[k] = 0u;
         for (int n = 0;; ++n) {
@@ -800,26 +800,33 @@ k_line_vv(const __grid_constant__ LineVVArgs L, const __grid_constant__ CUtensor
             // i < NBS; at the top of a column also g = 0..NBH-1 (rows [0, HP)).  One block per group of 8 lanes; the arm
             // words are requested now and turned into masks in the next trip (their latency stays off the tile cadence).
             uint32_t nxt[B];
-            int my_slot = -1;
+            int my_slot = -1, my_r0 = 0;
             {
                 const int nb = valid ? NBS + (j == 0 ? NBH : 0) : 0;
                 const int i = mask_lane_block<8>(pw, lane, nb);
                 const int g = (j == 0 ? 0 : NBH + j * NBS) + i;
                 if (i >= 0) my_slot = (colbase + g) % kVVMaskRing;
+                my_r0 = g * B;
 #pragma unroll
                 for (int k = 0; k < B; ++k) {
                     const int r = g * B + k;
                     nxt[k] = 0u;
-                    if (i >= 0 && r < H) nxt[k] = arm_cut_v(__ldg(a.arms[vslot] + (size_t)r * W + col), r, H);
+                    if (i >= 0 && r < H) nxt[k] = __ldg(a.arms[vslot] + (size_t)r * W + col);
                 }
             }
             if (pend_bar) {
-                if (pend_slot >= 0) masks_from_arms<B, true, 8>(sMask + (size_t)pend_slot * FR, sBounds + pend_slot, cur, HP, lane);
+                if (pend_slot >= 0) {
+                    // (the cut is applied here, a trip after the request, not on the fresh load: the request's latency
+                    // must stay off this loop)
+#pragma unroll
+                    for (int k = 0; k < B; ++k) cur[k] = arm_cut_v(cur[k], pend_r0 + k, H);
+                    masks_from_arms<B, true, 8>(sMask + (size_t)pend_slot * FR, sBounds + pend_slot, cur, HP, lane);
+                }
                 mbar_arrive(pend_bar);
             }
 #pragma unroll
             for (int k = 0; k < B; ++k) cur[k] = nxt[k];
-            pend_bar = fullH(st); pend_slot = my_slot;
+            pend_bar = fullH(st); pend_slot = my_slot; pend_r0 = my_r0;
             if (!valid) {
                 mbar_arrive(fullH(st));
                 break;
