@@ -403,7 +403,7 @@ def rowband_record(steps, warmup):
             "bit_exact": bool(chk) and all(chk.values()), "check": chk,
             "phase_ms": res["phase_ms_max_over_ranks"], "transport": res["transport"],
             "band_rows": res["band_rows"], "sub_image_rows": res["sub_image_rows"], "halo_rows": res["halo_rows"],
-            "arena_gb_per_gpu": res["arena_gb_per_gpu"], "steps": res["steps"]}
+            "vertical_passes": res.get("vertical_passes"), "arena_gb_per_gpu": res["arena_gb_per_gpu"], "steps": res["steps"]}
 
 
 def main():
