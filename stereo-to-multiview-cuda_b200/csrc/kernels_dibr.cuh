@@ -49,6 +49,59 @@ k_bleed(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, float *__rest
     if (mask) mask[(size_t)ty * W + tx] = (r == 1) ? 1.0f : 0.0f;
 }
 
+// k_occl, k_bleed (radius 1) and the mask conversion of BOTH views for one image row per block: the occlusion marks
+// of a row come from that row's disparities alone, so the three rows the 3x3 bleed reads are formed in shared memory
+// ([2 views][3 rows][W] bytes) and only the two float masks are written -- one launch instead of two memsets and
+// three kernels over four byte planes.  Row and column reflection exactly as k_bleed's.  H >= 3.
+__global__ void __launch_bounds__(256)
+k_occl_bleed_mask_row(const float *__restrict__ dispL, const float *__restrict__ dispR, float *__restrict__ maskL,
+                      float *__restrict__ maskR, int H, int W)
+{
+    extern __shared__ uint8_t occ_sm[];
+    const int ty = blockIdx.x;
+    uint8_t *oL = occ_sm, *oR = occ_sm + 3 * (size_t)W;  // [k][x], k = 0..2 <-> dy = -1..1
+    for (int i = threadIdx.x; i < 6 * W; i += blockDim.x) occ_sm[i] = 0;
+    __syncthreads();
+    int rows[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int y = k - 1;
+        int sy = ty + y;
+        if (sy < 0) sy = -sy;
+        if (sy > H - 1) sy = H - 1 - y;
+        rows[k] = sy;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const size_t row = (size_t)rows[k] * W;
+        for (int x = threadIdx.x; x < W; x += blockDim.x) {
+            int sd = (int)__fmul_rn(dispL[row + x], 1.0f);
+            oR[k * W + clampi(x + sd, 0, W - 1)] = 1;  // every writer stores 1: order-free
+            sd = (int)__fmul_rn(dispR[row + x], -1.0f);
+            oL[k * W + clampi(x + sd, 0, W - 1)] = 1;
+        }
+    }
+    __syncthreads();
+    const size_t row = (size_t)ty * W;
+    for (int tx = threadIdx.x; tx < W; tx += blockDim.x) {
+        int cl = 0, cr = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int x = -1; x <= 1; ++x) {
+                int sx = tx + x;
+                if (sx < 0) sx = -sx;
+                if (sx > W - 1) sx = W - 1 - x;
+                cl += oL[k * W + sx] > 0;
+                cr += oR[k * W + sx] > 0;
+            }
+        // (double)count > (9 - 1) * 0.30 = 2.4
+        const uint8_t rl = cl > 2 ? (uint8_t)1 : oL[W + tx], rr = cr > 2 ? (uint8_t)1 : oR[W + tx];
+        maskL[row + tx] = rl == 1 ? 1.0f : 0.0f;
+        maskR[row + tx] = rr == 1 ? 1.0f : 0.0f;
+    }
+}
+
 __global__ void k_occl_to_mask(const uint8_t *__restrict__ occl, float *__restrict__ mask, size_t n)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,6 +1,7 @@
 // kernels_refine.cuh — disparity refinement: left/right cross-check with
 // disocclusion labelling, iterative region voting, bilateral filter.
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace s2mv {
@@ -34,6 +35,38 @@ k_dcc_merge(uint8_t *__restrict__ outL, uint8_t *__restrict__ outR, const uint8_
     if (i >= n) return;
     if (outL[i] == 1 && disL[i] == 1) outL[i] = 2;
     if (outR[i] == 1 && disR[i] == 1) outR[i] = 2;
+}
+
+// The same three steps (flags cleared / dis-occlusion marks set, cross-check + marks, merge) for one image ROW per
+// block: a pixel's check reads and marks only its own row, so the marks live in shared memory and the whole stage is
+// one launch that writes each outlier byte once -- instead of four memsets and two kernels (k_dcc, k_dcc_merge: kept
+// for rows that do not fit shared memory).  sm: [2][W] bytes.
+__global__ void __launch_bounds__(256)
+k_dcc_row(const float *__restrict__ dispL, const float *__restrict__ dispR, uint8_t *__restrict__ outL,
+          uint8_t *__restrict__ outR, int H, int W)
+{
+    extern __shared__ uint8_t dis_sm[];
+    uint8_t *disL = dis_sm, *disR = dis_sm + W;
+    const size_t row = (size_t)blockIdx.x * W;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) { disL[x] = 1; disR[x] = 1; }
+    __syncthreads();
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        const float dl = dispL[row + x];
+        disR[clampi(x + (int)dl, 0, W - 1)] = 0;  // every writer stores 0: order-free
+        const float dr = dispR[row + x];
+        disL[clampi(x - (int)dr, 0, W - 1)] = 0;
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        float d = dispL[row + x];
+        int c = clampi(x + (int)d, 0, W - 1);
+        const bool ol = fabsf(__fsub_rn(d, dispR[row + c])) > 1.0f;
+        d = dispR[row + x];
+        c = clampi(x - (int)d, 0, W - 1);
+        const bool orr = fabsf(__fsub_rn(d, dispL[row + c])) > 1.0f;
+        outL[row + x] = ol ? (disL[x] ? 2 : 1) : 0;
+        outR[row + x] = orr ? (disR[x] ? 2 : 1) : 0;
+    }
 }
 
 // ---- iterative region voting (d_dr_irv.cu:17-43,134-269) -----------------
@@ -71,6 +104,10 @@ struct IrvArgs {
     // what the remaining iterations and the filters after them can still carry into the own rows (s2mv_api.cu)
     int row_lo, row_hi;
     int dense_min;       // list length from which an iteration takes the dense path
+    // k_irv_sparse_all (all iterations in one cooperative launch): iterations, and the row range as launch_irv derives it
+    // per iteration -- rows within post_reach + usd * (iterations - 1 - it) of [keep0, keep1) (keep1 < 0: all rows)
+    int iterations, keep0, keep1, post_reach;
+    int *hint;           // mapped host memory, [view]: length of the first iteration's list (read by the NEXT frame's host code)
     int col_votes;       // > 0: dense iterations vote column by column (k_irv_vote_col), this many columns (1..4) per
                          // ticket; vote[] is then indexed by PIXEL
 };
@@ -133,27 +170,20 @@ k_irv_compact(const IrvArgs a)
 
 constexpr int kIrvWarps = 8;
 
-__global__ void __launch_bounds__(kIrvWarps * 32)
-k_irv_vote(const IrvArgs a)
+// One outlier's vote by the sparse rule (one warp; hist: the warp's nbins counters in shared memory): the body of
+// k_irv_vote and of k_irv_sparse_all.  Returns through vote_out (lane 0 writes).
+__device__ __forceinline__ void irv_vote_entry(const IrvArgs &a, int v, int pix, int row_lo, int row_hi, int *hist, int lane,
+                                               int *vote_out)
 {
-    extern __shared__ int hist_all[];  // [kIrvWarps][nbins]
-    const int v = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int *hist = hist_all + warp * a.nbins;
-    if (irv_settled(a, v)) return;
-    const int count = *a.count[v];
-    if (blockIdx.x == 0 && threadIdx.x == 0) *a.next_count[v] = 0;  // consumed by k_irv_apply, which runs after
-    if (a.hseg[v] && count >= a.dense_min) return;                  // this iteration is k_irv_vote_dense's
     const float *__restrict__ disp = a.disp[v];
     const uint8_t *__restrict__ outl = a.outliers[v];
     const uint32_t *__restrict__ arms = a.arms[v];
     const int W = a.W;
-    for (int e = blockIdx.x * kIrvWarps + warp; e < count; e += gridDim.x * kIrvWarps) {
-        const int pix = a.list[v][e];
+    {
         const int gy = pix / W, gx = pix - gy * W;
-        if (gy < a.row_lo || gy >= a.row_hi) {  // not voted in this iteration (row band: cannot reach the own rows any more)
-            if (lane == 0) a.vote[v][e] = kNoVote;
-            continue;
+        if (gy < row_lo || gy >= row_hi) {  // not voted in this iteration (row band: cannot reach the own rows any more)
+            if (lane == 0) *vote_out = kNoVote;
+            return;
         }
         for (int b = lane; b < a.nbins; b += 32) hist[b] = 0;
         __syncwarp();
@@ -213,9 +243,25 @@ k_irv_vote(const IrvArgs a)
             int max_d = (best > 0) ? (bestb - a.zd) : (int)disp[pix];
             // dr_irv_kernel_3: ratio test on the histogram INDEX (Q16)
             bool ok = cnt > a.thresh_s && __fdiv_rn((float)(max_d + a.zd), (float)cnt) > a.thresh_h;
-            a.vote[v][e] = ok ? max_d : kNoVote;
+            *vote_out = ok ? max_d : kNoVote;
         }
     }
+}
+
+__global__ void __launch_bounds__(kIrvWarps * 32)
+k_irv_vote(const IrvArgs a)
+{
+    extern __shared__ int hist_all[];  // [kIrvWarps][nbins]
+    const int v = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int *hist = hist_all + warp * a.nbins;
+    if (irv_settled(a, v)) return;
+    const int count = *a.count[v];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.next_count[v] = 0;  // consumed by k_irv_apply, which runs after
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.it == 0 && a.hint) a.hint[v] = count;  // for the next frame's host code
+    if (a.hseg[v] && count >= a.dense_min) return;                  // this iteration is k_irv_vote_dense's
+    for (int e = blockIdx.x * kIrvWarps + warp; e < count; e += gridDim.x * kIrvWarps)
+        irv_vote_entry(a, v, a.list[v][e], a.row_lo, a.row_hi, hist, lane, a.vote[v] + e);
 }
 
 // ---- dense path ------------------------------------------------------------
@@ -598,6 +644,70 @@ k_irv_apply(const IrvArgs a)
     if (a.accepted[v] != nullptr) {
         taken = __reduce_add_sync(0xffffffffu, taken);
         if ((threadIdx.x & 31) == 0 && taken) atomicAdd(a.accepted[v] + a.it, taken);
+    }
+}
+
+// ---- every iteration in one launch (light frames) ---------------------------
+// A frame with few outliers spends region voting on launches: five iterations x (vote, apply) of a few microseconds
+// each, most of them returning at once after the iteration that accepted nothing.  This kernel is the sparse path of
+// all iterations in ONE cooperative launch -- vote, grid barrier, apply, grid barrier -- with the same vote per outlier
+// (irv_vote_entry), the same snapshot semantics (votes of an iteration read the state the previous one left) and the
+// same stop rule.  The host launches it when the PREVIOUS frame's list was short (a.hint, written here and by
+// k_irv_vote); it is exact whatever the list length, only slower than the dense path on a long list.
+__global__ void __launch_bounds__(kIrvWarps * 32)
+k_irv_sparse_all(IrvArgs a)
+{
+    extern __shared__ int hist_all[];  // [kIrvWarps][nbins]
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    const int v = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int *hist = hist_all + warp * a.nbins;
+    int *list = a.list[v], *next = a.next[v], *count_p = a.count[v], *next_count_p = a.next_count[v];
+    bool settled = false;
+    for (int it = 0; it < a.iterations; ++it) {
+        int row_lo = 0, row_hi = a.H;
+        if (a.keep1 >= 0) {
+            const int m = a.post_reach + a.usd * (a.iterations - 1 - it);
+            row_lo = max(0, a.keep0 - m);
+            row_hi = min(a.H, a.keep1 + m);
+        }
+        const int count = settled ? 0 : *count_p;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            *next_count_p = 0;
+            if (it == 0 && a.hint) a.hint[v] = count;
+        }
+        for (int e = blockIdx.x * kIrvWarps + warp; e < count; e += gridDim.x * kIrvWarps)
+            irv_vote_entry(a, v, list[e], row_lo, row_hi, hist, lane, a.vote[v] + e);
+        grid.sync();
+        // apply (k_irv_apply): accepted votes clear the outlier, the others form the next list
+        int taken = 0;
+        const int stride = gridDim.x * blockDim.x;
+        for (int e0 = blockIdx.x * blockDim.x; e0 < count; e0 += stride) {  // block-uniform trip count
+            const int e = e0 + threadIdx.x;
+            int pix = -1;
+            if (e < count) {
+                pix = list[e];
+                const int vote = a.vote[v][e];
+                if (vote != kNoVote) {
+                    a.outliers[v][pix] = 0;
+                    a.disp[v][pix] = (float)vote;
+                    pix = -1;
+                    ++taken;
+                }
+            }
+            const int pos = warp_append_base(next_count_p, pix >= 0 ? 1 : 0);
+            if (pix >= 0) next[pos] = pix;
+        }
+        taken = __reduce_add_sync(0xffffffffu, taken);
+        if (lane == 0 && taken) atomicAdd(a.accepted[v] + it, taken);
+        grid.sync();
+        // an iteration that accepted nothing leaves the state as it was: the later ones would repeat it
+        if (!settled && a.accepted[v][it] == 0) settled = true;
+        bool any_alive = false;  // the same answer in every block of the grid: they leave together
+        for (int vv = 0; vv < (int)gridDim.y; ++vv) any_alive |= a.accepted[vv][it] != 0;
+        if (!any_alive) break;
+        int *t = list; list = next; next = t;
+        t = count_p; count_p = next_count_p; next_count_p = t;
     }
 }
 

@@ -343,6 +343,12 @@ struct s2mv_ctx {
     const void *host_last[4] = {};  // the previous synchronous call's four caller buffers (auto mode)
     // test / A-B hooks read from the environment once, at create time
     int env_irv_dense_min = -1;     // S2MV_IRV_DENSE_MIN (-1: not set)
+    bool env_dcc_split = false;     // S2MV_DCC_SPLIT: cross-check and occlusion marks as memsets + separate kernels over byte planes
+                                    // (the forms for rows beyond shared memory) instead of the one-row-per-block kernels
+    int env_irv_coop = 1;           // S2MV_IRV_COOP: 0 never / 1 when the previous frame's lists were short / 2 always
+    int *irv_hint_h = nullptr, *irv_hint_d = nullptr;  // mapped host memory: [view] first-iteration list length of the last frame
+    int irv_coop_bps = 0;           // co-resident blocks per SM of k_irv_sparse_all (0: not asked yet, < 0: no cooperative launch)
+    size_t irv_coop_smem = 0;
     int env_irv_colw = 1;           // S2MV_IRV_COLW: columns per ticket of k_irv_vote_col (1..4; 1 measured best)
     bool env_irv_list_votes = false; // S2MV_IRV_LIST_VOTES: dense iterations vote per list entry (k_irv_vote_dense), not per column
     bool env_bilateral_scalar = false;  // S2MV_BILATERAL_SCALAR
@@ -422,6 +428,8 @@ static void free_arena(s2mv_ctx *c)
     c->band_flags = nullptr;
     if (c->band_status_h) cudaFreeHost(c->band_status_h);
     c->band_status_h = c->band_status_d = nullptr;
+    if (c->irv_hint_h) cudaFreeHost(c->irv_hint_h);
+    c->irv_hint_h = c->irv_hint_d = nullptr;
     for (void *p : c->allocs) cudaFree(p);
     c->allocs.clear();
     c->arena_bytes = 0;
@@ -454,6 +462,8 @@ extern "C" int s2mv_create(s2mv_ctx **out, int device)
     s2mv_ctx *c = new s2mv_ctx();
     if (const char *e = getenv("S2MV_IRV_DENSE_MIN")) c->env_irv_dense_min = atoi(e) < 0 ? 0 : atoi(e);
     if (const char *e = getenv("S2MV_IRV_LIST_VOTES")) c->env_irv_list_votes = atoi(e) != 0;
+    if (const char *e = getenv("S2MV_DCC_SPLIT")) c->env_dcc_split = atoi(e) != 0;
+    if (const char *e = getenv("S2MV_IRV_COOP")) c->env_irv_coop = std::min(2, std::max(0, atoi(e)));
     if (const char *e = getenv("S2MV_IRV_COLW")) c->env_irv_colw = std::min(4, std::max(1, atoi(e)));
     if (const char *e = getenv("S2MV_BILATERAL_SCALAR")) c->env_bilateral_scalar = atoi(e) != 0;
     if (const char *e = getenv("S2MV_LINE_V1")) c->env_line_v1 = atoi(e) != 0;
@@ -781,6 +791,11 @@ static int configure_impl(s2mv_ctx *c, const s2mv_params *p, const BandSpec *ban
         CU(cudaHostAlloc((void **)&c->band_status_h, sizeof(unsigned int), cudaHostAllocMapped));
         *c->band_status_h = 0;
         CU(cudaHostGetDevicePointer((void **)&c->band_status_d, c->band_status_h, 0));
+    }
+    {   // list lengths of the last frame's region voting, written by its kernels for the next frame's launch decision
+        CU(cudaHostAlloc((void **)&c->irv_hint_h, 2 * sizeof(int), cudaHostAllocMapped));
+        c->irv_hint_h[0] = c->irv_hint_h[1] = -1;
+        CU(cudaHostGetDevicePointer((void **)&c->irv_hint_d, c->irv_hint_h, 0));
     }
     TRY(dev_alloc_t(c, &c->tmask, n));
     TRY(dev_alloc_t(c, &c->lutAd, 768));
@@ -1164,6 +1179,12 @@ static int launch_costvol(s2mv_ctx *c, float *dispL, float *dispR, cudaStream_t 
 static int launch_dcc(s2mv_ctx *c, const float *dL, const float *dR, uint8_t *oL, uint8_t *oR, int H, int W, cudaStream_t st)
 {
     const size_t n = (size_t)H * W;
+    if (2 * (size_t)W <= 48 * 1024 && !c->env_dcc_split) {  // one launch, the marks of a row in shared memory
+        k_dcc_row<<<H, 256, 2 * (size_t)W, st>>>(dL, dR, oL, oR, H, W);
+        KCHECK();
+        c->launches += 1;
+        return S2MV_OK;
+    }
     CU(cudaMemsetAsync(oL, 0, n, st));
     CU(cudaMemsetAsync(oR, 0, n, st));
     CU(cudaMemsetAsync(c->disoccl[0], 1, n, st));
@@ -1215,9 +1236,42 @@ static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2],
         a.hseg[v] = dense_ok ? c->irv_hseg[v] : nullptr;
         a.stamp[v] = dense_ok ? c->irv_stamp[v] : nullptr;
         a.hchg[v] = dense_ok ? c->irv_hchg[v] : nullptr;
-        if (dense_ok && iterations > 1 && iterations < 255) CU(cudaMemsetAsync(c->irv_stamp[v], 0, n, st));
     }
     if (iterations >= 255) for (int v = 0; v < nviews; ++v) a.stamp[v] = nullptr;
+    a.iterations = iterations; a.keep0 = keep0; a.keep1 = keep1; a.post_reach = post_reach;
+    a.hint = c->irv_hint_d;
+    if (c->env_irv_coop && iterations <= 64 && c->irv_coop_bps >= 0) {
+        // All iterations in one cooperative launch when the lists are expected to be short: the previous frame's were
+        // (a scene cut costs one slow frame, not a wrong one), or there is no dense path to prefer on long ones.
+        bool light = c->env_irv_coop == 2 || !dense_ok;
+        if (!light && c->irv_hint_h) {
+            light = true;
+            for (int v = 0; v < nviews; ++v) {
+                const int h = ((volatile int *)c->irv_hint_h)[v];
+                if (h < 0 || h >= a.dense_min) light = false;
+            }
+        }
+        if (light) {
+            if (c->irv_coop_bps == 0 || c->irv_coop_smem != hist_bytes) {
+                int coop = 0, bps = 0;
+                CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+                if (coop) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_irv_sparse_all, kIrvWarps * 32, hist_bytes));
+                c->irv_coop_bps = bps > 0 ? bps : -1;
+                c->irv_coop_smem = hist_bytes;
+            }
+            if (c->irv_coop_bps > 0) {
+                for (int v = 0; v < nviews; ++v) { a.hseg[v] = nullptr; a.stamp[v] = nullptr; a.hchg[v] = nullptr; }
+                const int gx = std::max(1, std::min(c->sm_count * 4, c->sm_count * c->irv_coop_bps / nviews));
+                void *args[] = {&a};
+                CU(cudaLaunchCooperativeKernel((const void *)k_irv_sparse_all, dim3(gx, nviews), dim3(kIrvWarps * 32), args,
+                                               hist_bytes, st));
+                c->launches += 1;
+                return S2MV_OK;
+            }
+        }
+    }
+    if (dense_ok && iterations > 1 && iterations < 255)
+        for (int v = 0; v < nviews; ++v) CU(cudaMemsetAsync(c->irv_stamp[v], 0, n, st));
     a.col_votes = dense_ok && !c->env_irv_list_votes && usd <= 64 ? c->env_irv_colw : 0;
     for (int it = 0; it < iterations; ++it) {
         a.it = it;
@@ -1437,16 +1491,23 @@ static int run_dibr(s2mv_ctx *c, const float *fl, const float *fr, uint8_t *d_in
     const int H = p.num_rows, W = p.num_cols, V = p.num_views;
     const size_t n = (size_t)H * W;
     // DIBR (d_io.cu:160-191)
-    CU(cudaMemsetAsync(c->occl[0], 0, n, st));
-    CU(cudaMemsetAsync(c->occl[1], 0, n, st));
-    dim3 g((W + 255) / 256, H);
-    k_occl<<<g, 256, 0, st>>>(fl, fr, c->occl[0], c->occl[1], H, W);
-    KCHECK();
-    for (int v = 0; v < 2; ++v) {
-        k_bleed<<<g, 256, 0, st>>>(c->occl[v], c->occlB[v], c->mask[v], 1, H, W);
+    if (H >= 3 && W >= 2 && 6 * (size_t)W <= 48 * 1024 && !c->env_dcc_split) {
+        // occlusion marks, bleed and mask conversion of both views, one row per block (marks in shared memory)
+        k_occl_bleed_mask_row<<<H, 256, 6 * (size_t)W, st>>>(fl, fr, c->mask[0], c->mask[1], H, W);
         KCHECK();
+        c->launches += 1;
+    } else {
+        CU(cudaMemsetAsync(c->occl[0], 0, n, st));
+        CU(cudaMemsetAsync(c->occl[1], 0, n, st));
+        dim3 g((W + 255) / 256, H);
+        k_occl<<<g, 256, 0, st>>>(fl, fr, c->occl[0], c->occl[1], H, W);
+        KCHECK();
+        for (int v = 0; v < 2; ++v) {
+            k_bleed<<<g, 256, 0, st>>>(c->occl[v], c->occlB[v], c->mask[v], 1, H, W);
+            KCHECK();
+        }
+        c->launches += 3;
     }
-    c->launches += 3;
     TRY(launch_gauss(c, c->mask[1], c->tmask, c->gauss_kernel, c->h_gauss_kernel.data(), p.mask_blur_radius, 1, H, W,
                      st));
     if (V > 2) {

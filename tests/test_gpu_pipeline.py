@@ -237,6 +237,36 @@ def test_region_voting_dense_and_sparse_paths_agree_with_oracle(s2mv, oracle, bu
         assert_frame_equal(got, want)
 
 
+@pytest.mark.parametrize("coop", ["0", "1", "2"])
+def test_region_voting_in_one_cooperative_launch_agrees_with_oracle(s2mv, oracle, bud_sbs, coop, monkeypatch):
+    # light frames run all voting iterations in ONE cooperative launch (k_irv_sparse_all) once the previous frame's
+    # outlier lists were short (1, the default); 2 forces it on every frame -- also the outlier-heavy one --, 0 never
+    # uses it.  Same frames, same bar; the repeated light frame is the one that takes the hinted path.
+    from s2mv_b200_pkg import synth
+    monkeypatch.setenv("S2MV_IRV_COOP", coop)
+    with s2mv.Pipeline(0) as p:
+        sbs = np.ascontiguousarray(np.concatenate([bud_sbs[100:228, :320], bud_sbs[100:228, 640:960]], 1))
+        for _ in range(3):
+            got, want = run_both(p, oracle, sbs, 320, 96, 40)
+            assert_frame_equal(got, want)
+        got, want = run_both(p, oracle, synth.make_sbs(120, 352, 77), 352, 48, 24)   # after light frames: a "scene cut"
+        assert_frame_equal(got, want)
+
+
+def test_cross_check_and_occlusion_marks_as_separate_kernels_agree_with_oracle(s2mv, oracle, bud_sbs, monkeypatch):
+    # the frame call forms the cross-check labels and the occlusion masks one image row per block (marks in shared
+    # memory: k_dcc_row, k_occl_bleed_mask_row); the memset + kernel-per-step forms they replaced serve rows beyond
+    # shared memory and are held to the same bar here
+    from s2mv_b200_pkg import synth
+    monkeypatch.setenv("S2MV_DCC_SPLIT", "1")
+    with s2mv.Pipeline(0) as p:
+        got, want = run_both(p, oracle, synth.make_sbs(120, 352, 77), 352, 48, 24)
+        assert_frame_equal(got, want)
+        sbs = np.ascontiguousarray(np.concatenate([bud_sbs[100:228, :320], bud_sbs[100:228, 640:960]], 1))
+        got, want = run_both(p, oracle, sbs, 320, 96, 40)
+        assert_frame_equal(got, want)
+
+
 def test_bilateral_scalar_kernel_agrees_with_oracle(s2mv, oracle, bud_sbs, monkeypatch):
     # the frame call runs the paired (f32x2) bilateral kernel; the one-output-at-a-time kernel it replaced stays
     # selectable and is held to the same bar on the same frame
