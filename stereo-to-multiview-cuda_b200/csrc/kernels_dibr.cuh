@@ -164,39 +164,67 @@ k_gauss_dilate4(const float *__restrict__ in, float *__restrict__ out, const flo
     float *tile = gsm4, *sk = tile + TWP * TH;
     const int tid = threadIdx.y * 32 + threadIdx.x;
     const int bx = blockIdx.x * kGa4W, by = blockIdx.y * kGa4H;
+    // Masks are 0/1 planes with the occlusions as islands: most tiles, halo included, hold one value.  Every output
+    // of such a tile is the same number -- the same 441 operations on the same operands -- so one thread forms it
+    // (with the same loop, not a closed form) and the block stores it.
+    float first = 0.0f;
+    int same = 1;
     for (int i = tid; i < TWP * TH; i += 256) {
         const int ty = i / TWP, tx = i - ty * TWP;
         const float v = in[(size_t)clampi(by + ty - R, 0, H - 1) * W + clampi(bx + tx - R, 0, W - 1)];
-        tile[i] = invert ? __fsub_rn(1.0f, v) : v;
+        const float t = invert ? __fsub_rn(1.0f, v) : v;
+        tile[i] = t;
+        if (i == tid) first = t;
+        same &= (__float_as_uint(t) == __float_as_uint(first));
     }
     for (int i = tid; i < KWP * KW; i += 256) {
         const int ky = i / KWP, kx = i - ky * KWP;
         sk[i] = kx < KW ? kernel[ky * KW + kx] : 0.0f;
     }
     __syncthreads();
+    const bool uniform = __syncthreads_and(same && __float_as_uint(first) == __float_as_uint(tile[0])) != 0;
     const int x0 = 4 * threadIdx.x, gx = bx + x0, gy = by + threadIdx.y;
-    if (gx >= W || gy >= H) return;
+    const bool inside = gx < W && gy < H;
+    __shared__ float uni_q;
     float res[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (uniform ? tid == 0 : inside) {
 #pragma unroll 1
-    for (int ky = 0; ky < KW; ++ky) {
-        float v[NV], w[KWP];
-        const float4 *trow = reinterpret_cast<const float4 *>(tile + (threadIdx.y + ky) * TWP + x0);
-        const float4 *wrow = reinterpret_cast<const float4 *>(sk + ky * KWP);
+        for (int ky = 0; ky < KW; ++ky) {
+            float v[NV], w[KWP];
+            const float4 *trow = reinterpret_cast<const float4 *>(tile + (threadIdx.y + ky) * TWP + x0);
+            const float4 *wrow = reinterpret_cast<const float4 *>(sk + ky * KWP);
 #pragma unroll
-        for (int i = 0; i < NV / 4; ++i) {
-            const float4 t = trow[i];
-            v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-        }
+            for (int i = 0; i < NV / 4; ++i) {
+                const float4 t = trow[i];
+                v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+            }
 #pragma unroll
-        for (int i = 0; i < KWP / 4; ++i) {
-            const float4 t = wrow[i];
-            w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+            for (int i = 0; i < KWP / 4; ++i) {
+                const float4 t = wrow[i];
+                w[4 * i] = t.x; w[4 * i + 1] = t.y; w[4 * i + 2] = t.z; w[4 * i + 3] = t.w;
+            }
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int kx = 0; kx < KW; ++kx) res[o] = __fmaf_rn(v[o + kx], w[kx], res[o]);
         }
+    }
+    if (uniform) {
+        if (tid == 0) {  // its first output is every output of the tile
+            const float va = tile[R * TWP + R];
+            const float q = __fdiv_rn(res[0], norm);
+            uni_q = (va < q) ? q : va;
+        }
+        __syncthreads();
+        if (!inside) return;
+        const float q = uni_q;
+        float *o4 = out + (size_t)gy * W + gx;
 #pragma unroll
         for (int o = 0; o < 4; ++o)
-#pragma unroll
-            for (int kx = 0; kx < KW; ++kx) res[o] = __fmaf_rn(v[o + kx], w[kx], res[o]);
+            if (gx + o < W) o4[o] = q;
+        return;
     }
+    if (!inside) return;
     float *o4 = out + (size_t)gy * W + gx;
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
