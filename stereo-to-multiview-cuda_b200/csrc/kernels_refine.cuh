@@ -864,56 +864,79 @@ k_bilateral4p(const float *__restrict__ in0, const float *__restrict__ in1, floa
     float *__restrict__ out = blockIdx.z ? out1 : out0;
     const int tid = threadIdx.y * 32 + threadIdx.x;
     const int bx = blockIdx.x * kBil4W, by = blockIdx.y * kBil4H;
+    // A tile that holds ONE disparity, halo included (flat regions; the whole frame of a pair of identical images),
+    // gives every output the same 225 operations on the same operands: one thread forms the value, the block stores it.
+    float first = 0.0f;
+    int same = 1;
     for (int i = tid; i < TWP * TH; i += 256) {
         const int ty = i / TWP, tx = i - ty * TWP;
         const float *row = in + (size_t)clampi(by + ty - R, 0, H - 1) * W;
-        tileA[i] = row[clampi(bx + tx - R, 0, W - 1)];
-        tileB[i] = row[clampi(bx + tx + 1 - R, 0, W - 1)];
+        const float va = row[clampi(bx + tx - R, 0, W - 1)], vb = row[clampi(bx + tx + 1 - R, 0, W - 1)];
+        tileA[i] = va;
+        tileB[i] = vb;
+        if (i == tid) first = va;
+        same &= (__float_as_uint(va) == __float_as_uint(first)) & (__float_as_uint(vb) == __float_as_uint(first));
     }
     for (int i = tid; i < ncolour; i += 256) scol[i] = colour[i];
     __syncthreads();
+    const bool uniform = __syncthreads_and(same && __float_as_uint(first) == __float_as_uint(tileA[0])) != 0;
     const int x0 = 4 * threadIdx.x, gx = bx + x0, gy = by + threadIdx.y;
-    if (gx >= W || gy >= H) return;
-    const float *centre = tileA + (threadIdx.y + R) * TWP + x0 + R;
-    const f32x2_t nva[2] = {pack2(-centre[0], -centre[1]), pack2(-centre[2], -centre[3])};
-    f32x2_t norm[2] = {pack2(0.0f, 0.0f), pack2(0.0f, 0.0f)}, res[2] = {norm[0], norm[0]};
+    const bool inside = gx < W && gy < H;
+    __shared__ float uni_out;
+    float r[4] = {0.f, 0.f, 0.f, 0.f}, nm[4] = {1.f, 1.f, 1.f, 1.f};
+    if (uniform ? tid == 0 : inside) {
+        const float *centre = tileA + (threadIdx.y + R) * TWP + x0 + R;
+        const f32x2_t nva[2] = {pack2(-centre[0], -centre[1]), pack2(-centre[2], -centre[3])};
+        f32x2_t norm[2] = {pack2(0.0f, 0.0f), pack2(0.0f, 0.0f)}, res[2] = {norm[0], norm[0]};
 #pragma unroll 1
-    for (int ky = 0; ky < KW; ++ky) {
-        f32x2_t pa[2 * NA], pb[2 * NB];
-        const ulonglong2 *arow = reinterpret_cast<const ulonglong2 *>(tileA + (threadIdx.y + ky) * TWP + x0);
-        const ulonglong2 *brow = reinterpret_cast<const ulonglong2 *>(tileB + (threadIdx.y + ky) * TWP + x0);
-        const float2 *wrow = wpairs.w[ky];
+        for (int ky = 0; ky < KW; ++ky) {
+            f32x2_t pa[2 * NA], pb[2 * NB];
+            const ulonglong2 *arow = reinterpret_cast<const ulonglong2 *>(tileA + (threadIdx.y + ky) * TWP + x0);
+            const ulonglong2 *brow = reinterpret_cast<const ulonglong2 *>(tileB + (threadIdx.y + ky) * TWP + x0);
+            const float2 *wrow = wpairs.w[ky];
 #pragma unroll
-        for (int i = 0; i < NA; ++i) {
-            const ulonglong2 t = arow[i];
-            pa[2 * i] = t.x; pa[2 * i + 1] = t.y;
-        }
+            for (int i = 0; i < NA; ++i) {
+                const ulonglong2 t = arow[i];
+                pa[2 * i] = t.x; pa[2 * i + 1] = t.y;
+            }
 #pragma unroll
-        for (int i = 0; i < NB; ++i) {
-            const ulonglong2 t = brow[i];
-            pb[2 * i] = t.x; pb[2 * i + 1] = t.y;
-        }
+            for (int i = 0; i < NB; ++i) {
+                const ulonglong2 t = brow[i];
+                pb[2 * i] = t.x; pb[2 * i + 1] = t.y;
+            }
 #pragma unroll
-        for (int op = 0; op < 2; ++op) {        // outputs (0,1), then (2,3)
+            for (int op = 0; op < 2; ++op) {        // outputs (0,1), then (2,3)
 #pragma unroll
-            for (int kx = 0; kx < KW; ++kx) {
-                // (v[2 op + kx], v[2 op + kx + 1]) of the row
-                const f32x2_t vs = (kx & 1) ? pb[op + (kx - 1) / 2] : pa[op + kx / 2];
-                float d0, d1;
-                unpack2(add2(vs, nva[op]), d0, d1);
-                const int c0 = __float_as_int(__fadd_rz(fabsf(d0), 2097152.0f)) & 0x7ffffc;
-                const int c1 = __float_as_int(__fadd_rz(fabsf(d1), 2097152.0f)) & 0x7ffffc;
-                const float s0 = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(scol) + c0);
-                const float s1 = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(scol) + c1);
-                const f32x2_t wt = mul2(pack2(wrow[kx].x, wrow[kx].y), pack2(s0, s1));
-                norm[op] = add2(norm[op], wt);
-                res[op] = fma2(vs, wt, res[op]);
+                for (int kx = 0; kx < KW; ++kx) {
+                    // (v[2 op + kx], v[2 op + kx + 1]) of the row
+                    const f32x2_t vs = (kx & 1) ? pb[op + (kx - 1) / 2] : pa[op + kx / 2];
+                    float d0, d1;
+                    unpack2(add2(vs, nva[op]), d0, d1);
+                    const int c0 = __float_as_int(__fadd_rz(fabsf(d0), 2097152.0f)) & 0x7ffffc;
+                    const int c1 = __float_as_int(__fadd_rz(fabsf(d1), 2097152.0f)) & 0x7ffffc;
+                    const float s0 = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(scol) + c0);
+                    const float s1 = *reinterpret_cast<const float *>(reinterpret_cast<const char *>(scol) + c1);
+                    const f32x2_t wt = mul2(pack2(wrow[kx].x, wrow[kx].y), pack2(s0, s1));
+                    norm[op] = add2(norm[op], wt);
+                    res[op] = fma2(vs, wt, res[op]);
+                }
             }
         }
+        unpack2(res[0], r[0], r[1]); unpack2(res[1], r[2], r[3]);
+        unpack2(norm[0], nm[0], nm[1]); unpack2(norm[1], nm[2], nm[3]);
     }
-    float r[4], nm[4];
-    unpack2(res[0], r[0], r[1]); unpack2(res[1], r[2], r[3]);
-    unpack2(norm[0], nm[0], nm[1]); unpack2(norm[1], nm[2], nm[3]);
+    if (uniform) {
+        if (tid == 0) uni_out = __fdiv_rn(r[0], nm[0]);  // thread 0's first output is every output of the tile
+        __syncthreads();
+        if (!inside) return;
+        const float q = uni_out;
+        float *o4 = out + (size_t)gy * W + gx;
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            if (gx + o < W) o4[o] = q;
+        return;
+    }
+    if (!inside) return;
     float *o4 = out + (size_t)gy * W + gx;
 #pragma unroll
     for (int o = 0; o < 4; ++o)
