@@ -349,6 +349,7 @@ struct s2mv_ctx {
     int *irv_hint_h = nullptr, *irv_hint_d = nullptr;  // mapped host memory: [view] first-iteration list length of the last frame
     int irv_coop_bps = 0;           // co-resident blocks per SM of k_irv_sparse_all (0: not asked yet, < 0: no cooperative launch)
     size_t irv_coop_smem = 0;
+    bool env_irv_colw_set = false;  // S2MV_IRV_COLW given: the column walk whatever the image size (test hook)
     int env_irv_colw = 1;           // S2MV_IRV_COLW: columns per ticket of k_irv_vote_col (1..4; 1 measured best)
     bool env_irv_list_votes = false; // S2MV_IRV_LIST_VOTES: dense iterations vote per list entry (k_irv_vote_dense), not per column
     bool env_bilateral_scalar = false;  // S2MV_BILATERAL_SCALAR
@@ -464,7 +465,7 @@ extern "C" int s2mv_create(s2mv_ctx **out, int device)
     if (const char *e = getenv("S2MV_IRV_LIST_VOTES")) c->env_irv_list_votes = atoi(e) != 0;
     if (const char *e = getenv("S2MV_DCC_SPLIT")) c->env_dcc_split = atoi(e) != 0;
     if (const char *e = getenv("S2MV_IRV_COOP")) c->env_irv_coop = std::min(2, std::max(0, atoi(e)));
-    if (const char *e = getenv("S2MV_IRV_COLW")) c->env_irv_colw = std::min(4, std::max(1, atoi(e)));
+    if (const char *e = getenv("S2MV_IRV_COLW")) { c->env_irv_colw = std::min(4, std::max(1, atoi(e))); c->env_irv_colw_set = true; }
     if (const char *e = getenv("S2MV_BILATERAL_SCALAR")) c->env_bilateral_scalar = atoi(e) != 0;
     if (const char *e = getenv("S2MV_LINE_V1")) c->env_line_v1 = atoi(e) != 0;
     if (const char *e = getenv("S2MV_L2_CFG")) c->env_l2_cfg = std::min(3, std::max(0, atoi(e)));
@@ -1272,7 +1273,12 @@ static int launch_irv(s2mv_ctx *c, float *const disp[2], uint8_t *const outl[2],
     }
     if (dense_ok && iterations > 1 && iterations < 255)
         for (int v = 0; v < nviews; ++v) CU(cudaMemsetAsync(c->irv_stamp[v], 0, n, st));
-    a.col_votes = dense_ok && !c->env_irv_list_votes && usd <= 64 ? c->env_irv_colw : 0;
+    // the column walk hands out (column, 32-row strip) tickets, each a serial chain of up to 32 votes: it needs several
+    // tickets per resident warp to balance (640x384: 15 k tickets for 9.5 k warps, 0.48 ms against 0.42 ms by list entry)
+    const long long col_tickets = (long long)W * ((H + 31) / 32) * nviews;
+    const bool col_forced = c->env_irv_colw_set;
+    a.col_votes = dense_ok && !c->env_irv_list_votes && usd <= 64 && (col_forced || col_tickets >= 4ll * c->sm_count * 64)
+                      ? c->env_irv_colw : 0;
     for (int it = 0; it < iterations; ++it) {
         a.it = it;
         a.row_lo = 0;

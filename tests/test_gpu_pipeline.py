@@ -228,6 +228,7 @@ def test_region_voting_dense_and_sparse_paths_agree_with_oracle(s2mv, oracle, bu
     from s2mv_b200_pkg import synth
     monkeypatch.setenv("S2MV_IRV_DENSE_MIN", dense_min)
     monkeypatch.setenv("S2MV_IRV_LIST_VOTES", list_votes)
+    monkeypatch.setenv("S2MV_IRV_COLW", "1")     # the column walk also on these small frames (it is chosen by image size)
     with s2mv.Pipeline(0) as p:
         got, want = run_both(p, oracle, synth.make_sbs(120, 352, 77), 352, 48, 24)
         assert (want[3]["outliers_l"] != 0).mean() > 0.05
