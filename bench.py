@@ -413,6 +413,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-binding", action="store_true", help="N > 1: leave the ranks on the default CPU set")
     ap.add_argument("--no-extras", action="store_true", help="skip extra.* (other workloads, reference GPU timing, row bands)")
     ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
                     help="config2 (default, the headline): the bundled pair at 1080p; config3: synthetic 1080p stream")
@@ -432,6 +433,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
+    # several ranks on one host: each runs on the CPUs next to its GPU, so its pinned frame slots and the copies into
+    # them stay on that socket (one rank keeps all cores: it also times the CPU baseline)
+    cpus = sharding.bind_to_gpu_cpus(local_rank) if world > 1 and not args.no_cpu_binding else None
     sharding.init_process_group("nccl")
     K, Wm = args.steps, max(args.warmup, 3)
 
@@ -520,6 +524,7 @@ def main():
                                                                  "page_locked_in_place": pageable["registered"],
                                                                  "unit": "frames/s"}}},
         "gpu_launches": dres["launches"],
+        "host_cpus_per_rank": None if cpus is None else len(cpus),
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,

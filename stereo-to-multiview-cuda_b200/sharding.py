@@ -60,3 +60,34 @@ def aggregate_throughput(local_units, local_seconds, device=None):
     total = reduce_scalar(local_units, "sum", device)
     slowest = reduce_scalar(local_seconds, "max", device)
     return total / slowest if slowest > 0 else 0.0, total, slowest
+
+
+def parse_cpulist(text):
+    """'0-3,8,10-11' -> [0, 1, 2, 3, 8, 10, 11] (the format of sysfs cpulist files)."""
+    cpus = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_cpus(device_index, sysfs="/sys/bus/pci/devices"):
+    """One process per GPU: run this process on the CPUs next to its GPU (the PCI device's local_cpulist), so that the
+    pinned frame buffers it allocates afterwards (first touch) and the copies into them stay on that socket.  Returns
+    the CPU list, or None when the topology cannot be read or the binding is refused (nothing changes then)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        addr = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open(os.path.join(sysfs, addr, "local_cpulist")) as f:
+            cpus = parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # noqa: BLE001  (no sysfs entry, no permission, no such attribute: keep the default placement)
+        return None

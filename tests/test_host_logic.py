@@ -171,3 +171,26 @@ def test_gloo_halo_exchange_and_row_gather(s2mv, tmp_path, WORLD):
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, e
         assert "RESULT ok" in o
+
+
+def test_cpu_binding_reads_the_gpu_local_cpulist(s2mv, tmp_path, monkeypatch):
+    """sharding.bind_to_gpu_cpus: the PCI device's local_cpulist, intersected with the CPUs the process may use;
+    anything missing leaves the placement alone."""
+    import types
+    from s2mv_b200_pkg import sharding
+    assert sharding.parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert sharding.parse_cpulist("") == []
+    import torch
+    allowed = sorted(os.sched_getaffinity(0))
+    dev = tmp_path / "0000:1b:00.0"
+    dev.mkdir()
+    (dev / "local_cpulist").write_text("%d\n" % allowed[0])
+    monkeypatch.setattr(torch.cuda, "get_device_properties",
+                        lambda i: types.SimpleNamespace(pci_domain_id=0, pci_bus_id=0x1b, pci_device_id=0))
+    try:
+        assert sharding.bind_to_gpu_cpus(0, sysfs=str(tmp_path)) == [allowed[0]]
+        assert sorted(os.sched_getaffinity(0)) == [allowed[0]]
+    finally:
+        os.sched_setaffinity(0, allowed)
+    assert sharding.bind_to_gpu_cpus(0, sysfs=str(tmp_path / "nowhere")) is None
+    assert sorted(os.sched_getaffinity(0)) == allowed
