@@ -447,8 +447,10 @@ k_irv_vote_dense(const IrvArgs a)
 // An occluded region then costs about two 128-byte row reads per outlier instead of its arm length; sums of integer
 // counts, so the histogram -- and with it count, first maximum and vote -- is the one k_irv_vote_dense forms.
 // Votes are stored per PIXEL (k_irv_apply reads them there when col_votes is set).
+// 6 blocks per SM (40 registers): the walk is a chain of dependent loads per warp, so warps in flight are what hides
+// it -- 48 per SM against 32 took 8 % off the refinement of a config-3 frame; 64 (32 registers, spills) gave it back
 template <int NW>
-__global__ void __launch_bounds__(kIrvWarps * 32)
+__global__ void __launch_bounds__(kIrvWarps * 32, 6)
 k_irv_vote_col(const IrvArgs a)
 {
     const int v = blockIdx.y;
