@@ -323,7 +323,8 @@ k_irv_hseg(const IrvArgs a)
             if (gx < W) {
                 const uint32_t ar = arms[row + gx];
                 const int cl = arm_left(ar), cr = arm_right(ar);
-                for (int k = -cl; k <= cr; ++k) mine |= chg[t + a.usd + k];
+                if (cl > a.usd || cr > a.usd) mine = 1;  // arms from a caller (stage API) beyond usd: always rebuilt
+                else for (int k = -cl; k <= cr; ++k) mine |= chg[t + a.usd + k];
                 a.hchg[v][row + gx] = (uint8_t)mine;
             }
         }
@@ -336,9 +337,9 @@ k_irv_hseg(const IrvArgs a)
         if (gx < W && mine) {
             const uint32_t ar = arms[row + gx];
             const int cl = arm_left(ar), span = cl + arm_right(ar) + 1;  // inclusive [-L, R]
+            uint8_t *h = hs + t * pitch;
             const float *__restrict__ dp = disp + row + (gx - cl);
             const uint8_t *__restrict__ op = outl + row + (gx - cl);
-            uint8_t *h = hs + t * pitch;
             for (int k = 0; k < span; ++k)
                 if (op[k] == 0) h[clampi((int)dp[k] + a.zd, 0, a.nbins - 1)] += 1;
         }
@@ -524,7 +525,7 @@ k_irv_vote_col(const IrvArgs a)
                 if (incremental) {
                     // still listed = its last vote was rejected; with no changed span in its support it would be again
                     const int b0 = nlo - (ys - usd), b1 = nhi - (ys - usd);  // bit range, inclusive
-                    uint32_t hit = 0;
+                    uint32_t hit = b1 >= 32 + 2 * usd ? 1u : 0u;  // (a caller's arm beyond usd: outside the tracked rows)
 #pragma unroll
                     for (int k = 0; k < 5; ++k) {
                         const int s0 = max(b0 - 32 * k, 0), s1 = min(b1 - 32 * k, 31);
