@@ -238,6 +238,20 @@ def test_region_voting_dense_and_sparse_paths_agree_with_oracle(s2mv, oracle, bu
         assert_frame_equal(got, want)
 
 
+@pytest.mark.parametrize("colw", ["1", "3", "4"])
+def test_region_voting_column_walk_on_ragged_shapes(s2mv, oracle, colw, monkeypatch):
+    # the column walk with 1, 3 and 4 columns per ticket on widths that are not multiples of 4 (or of the ticket), a
+    # height that is not a multiple of the 32-row strips, and three histogram widths (128, 256 and 384 bins per pixel)
+    from s2mv_b200_pkg import synth
+    monkeypatch.setenv("S2MV_IRV_DENSE_MIN", "0")
+    monkeypatch.setenv("S2MV_IRV_COLW", colw)
+    with s2mv.Pipeline(0) as p:
+        for H, W, D, zd, seed in ((75, 203, 40, 17, 5), (41, 130, 200, 90, 6), (70, 97, 300, 150, 7)):
+            got, want = run_both(p, oracle, synth.make_sbs(H, W, seed), W, D, zd)
+            assert (want[3]["outliers_l"] != 0).mean() > 0.02
+            assert_frame_equal(got, want)
+
+
 @pytest.mark.parametrize("coop", ["0", "1", "2"])
 def test_region_voting_in_one_cooperative_launch_agrees_with_oracle(s2mv, oracle, bud_sbs, coop, monkeypatch):
     # light frames run all voting iterations in ONE cooperative launch (k_irv_sparse_all) once the previous frame's
