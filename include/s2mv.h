@@ -204,6 +204,10 @@ int s2mv_band_status(s2mv_ctx *ctx, void *stream);
  * flight; collect blocks until the oldest frame's outputs are on the host.
  *   s2mv_stream_input_buffer: the pinned input buffer the NEXT submit will
  *     use, so a decoder can write into it directly; then submit(ctx, NULL).
+ *   s2mv_stream_submit(ctx, img_sbs): a page-locked img_sbs (cudaHostAlloc /
+ *     cudaHostRegister) is copied to the device from where it lies and must
+ *     stay unchanged until that frame is collected; pageable memory is staged
+ *     through the slot's pinned buffer and may be reused at once.
  *   s2mv_stream_collect: copies into disp_l/disp_r/interlaced when non-NULL
  *     and/or returns the slot's pinned output buffers (valid until `depth`
  *     further submits). */

@@ -98,8 +98,18 @@ extern "C" int s2mv_stream_submit(s2mv_ctx *c, const uint8_t *img_sbs)
     const size_t sbs_bytes = (size_t)p.num_rows * c->stream_cols_sbs * 3;
     const size_t out_bytes = (size_t)p.num_rows_out * p.num_cols_out * 3;
     s2mv_ctx::StreamSlot &s = c->slots[c->slot_head];
-    if (img_sbs && img_sbs != s.h_sbs) memcpy(s.h_sbs, img_sbs, sbs_bytes);  // NULL / the slot's own buffer: already in place
-    CU(cudaMemcpyAsync(s.d_sbs, s.h_sbs, sbs_bytes, cudaMemcpyHostToDevice, c->st_in));
+    // NULL / the slot's own buffer: already in place.  A page-locked frame (cudaHostAlloc / cudaHostRegister'ed by the
+    // caller) is read by the copy engine where it lies -- it must stay unchanged until the frame is collected; any
+    // other frame is staged through the slot's pinned buffer.
+    const uint8_t *src = s.h_sbs;
+    if (img_sbs && img_sbs != s.h_sbs) {
+        cudaPointerAttributes at;
+        const bool locked = cudaPointerGetAttributes(&at, img_sbs) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        if (locked) src = img_sbs;
+        else memcpy(s.h_sbs, img_sbs, sbs_bytes);
+    }
+    CU(cudaMemcpyAsync(s.d_sbs, src, sbs_bytes, cudaMemcpyHostToDevice, c->st_in));
     CU(cudaEventRecord(s.ev_in, c->st_in));
     CU(cudaStreamWaitEvent(c->stream, s.ev_in, 0));
     TRY(run_frame(c, s.d_sbs, c->stream_cols_sbs, s.d_disp[0], s.d_disp[1], s.d_out, false, c->stream));

@@ -198,14 +198,18 @@ def test_frame_stream_matches_synchronous_call():
         with pytest.raises(s2mv_b200.S2mvError):
             p.stream_collect()                  # nothing in flight
         got = []
+        import torch
+        locked = {i: torch.from_numpy(f).pin_memory() for i, f in enumerate(frames) if i % 3 == 2}
         for i, f in enumerate(frames):
             if p.stream_pending == 3:
                 got.append(p.stream_collect())
-            if i % 2:
+            if i in locked:
+                p.stream_submit(locked[i].numpy())   # page-locked: copied to the device from where it lies
+            elif i % 2:
                 np.copyto(p.stream_input_buffer(), f)
                 p.stream_submit(None)
             else:
-                p.stream_submit(f)
+                p.stream_submit(f)                   # pageable: staged through the slot's pinned buffer
         assert p.stream_pending == 3
         with pytest.raises(s2mv_b200.S2mvError):
             p.stream_submit(frames[0])          # all slots in flight
