@@ -514,8 +514,15 @@ k_irv_vote_col(const IrvArgs a)
 #pragma unroll
             for (int w = 0; w < NW; ++w) lo[w] = hi[w] = 0u;
             int wlo = 0, whi = -1;  // rows in the window, inclusive; empty
-            const uint32_t *__restrict__ col = hseg + (size_t)gx * WPP + lane;
             const size_t rstride = (size_t)W * WPP;
+            const uint32_t *__restrict__ col = hseg + (size_t)gx * WPP + lane;
+            // rows wlo and whi of the column: the window is walked by pointer steps, not by a 64-bit multiply per row
+            const uint32_t *__restrict__ p_top = col, *__restrict__ p_bot = col;
+            // lane i keeps the count and key of the outlier in row ys + i; the votes of the strip are formed afterwards
+            // with the lanes side by side (the conversion, the division and the store once per strip, not per outlier)
+            int my_cnt = -1;
+            uint32_t my_key = 0;
+            const uint32_t m_all = m;
             while (m) {
                 const int i = __ffs(m) - 1;
                 m &= m - 1;
@@ -531,10 +538,7 @@ k_irv_vote_col(const IrvArgs a)
                         const int s0 = max(b0 - 32 * k, 0), s1 = min(b1 - 32 * k, 31);
                         if (s0 <= s1) hit |= chg[k] & ((0xffffffffu >> (31 - s1)) & (0xffffffffu << s0));
                     }
-                    if (!hit) {
-                        if (lane == 0) vote[(size_t)gy * W + gx] = kNoVote;
-                        continue;
-                    }
+                    if (!hit) continue;  // my_cnt of lane i stays -1: no vote
                 }
                 const int nrows = nhi - nlo + 1;
                 const bool slide = whi >= wlo && abs(nlo - wlo) + abs(nhi - whi) < nrows;
@@ -543,32 +547,32 @@ k_irv_vote_col(const IrvArgs a)
                     for (int w = 0; w < NW; ++w) lo[w] = hi[w] = 0u;
                     wlo = nlo;
                     whi = nlo - 1;
+                    p_top = col + (size_t)nlo * rstride;
+                    p_bot = p_top - rstride;
                 }
                 // rows that leave (above the new top / below the new bottom), then rows that enter
-                for (; wlo < nlo; ++wlo) {
-                    const uint32_t *p = col + (size_t)wlo * rstride;
+                for (; wlo < nlo; ++wlo, p_top += rstride) {
 #pragma unroll
                     for (int w = 0; w < NW; ++w) {
-                        const uint32_t x = __ldg(p + 32 * w);
+                        const uint32_t x = __ldg(p_top + 32 * w);
                         lo[w] -= x & 0x00ff00ffu;
                         hi[w] -= (x >> 8) & 0x00ff00ffu;
                     }
                 }
-                for (; whi > nhi; --whi) {
-                    const uint32_t *p = col + (size_t)whi * rstride;
+                for (; whi > nhi; --whi, p_bot -= rstride) {
 #pragma unroll
                     for (int w = 0; w < NW; ++w) {
-                        const uint32_t x = __ldg(p + 32 * w);
+                        const uint32_t x = __ldg(p_bot + 32 * w);
                         lo[w] -= x & 0x00ff00ffu;
                         hi[w] -= (x >> 8) & 0x00ff00ffu;
                     }
                 }
                 for (; wlo > nlo;) {
                     --wlo;
-                    const uint32_t *p = col + (size_t)wlo * rstride;
+                    p_top -= rstride;
 #pragma unroll
                     for (int w = 0; w < NW; ++w) {
-                        const uint32_t x = __ldg(p + 32 * w);
+                        const uint32_t x = __ldg(p_top + 32 * w);
                         lo[w] += x & 0x00ff00ffu;
                         hi[w] += (x >> 8) & 0x00ff00ffu;
                     }
@@ -576,10 +580,10 @@ k_irv_vote_col(const IrvArgs a)
 #pragma unroll 4
                 for (; whi < nhi;) {
                     ++whi;
-                    const uint32_t *p = col + (size_t)whi * rstride;
+                    p_bot += rstride;
 #pragma unroll
                     for (int w = 0; w < NW; ++w) {
-                        const uint32_t x = __ldg(p + 32 * w);
+                        const uint32_t x = __ldg(p_bot + 32 * w);
                         lo[w] += x & 0x00ff00ffu;
                         hi[w] += (x >> 8) & 0x00ff00ffu;
                     }
@@ -598,14 +602,22 @@ k_irv_vote_col(const IrvArgs a)
                 }
                 cnt = __reduce_add_sync(0xffffffffu, cnt);
                 key = __reduce_max_sync(0xffffffffu, key);
-                if (lane == 0) {
-                    const size_t pix = (size_t)gy * W + gx;
-                    const int best = (int)(key >> 10), bestb = 1023 - (int)(key & 1023u);
-                    int max_d = (best > 0) ? (bestb - a.zd) : (int)disp[pix];
-                    // dr_irv_kernel_3: ratio test on the histogram INDEX (Q16)
-                    bool ok = (int)cnt > a.thresh_s && __fdiv_rn((float)(max_d + a.zd), (float)(int)cnt) > a.thresh_h;
-                    vote[pix] = ok ? max_d : kNoVote;
+                if (lane == i) {
+                    my_cnt = (int)cnt;
+                    my_key = key;
                 }
+            }
+            if ((m_all >> lane) & 1u) {  // this lane's row holds an outlier of the column
+                const size_t pix = (size_t)y_l * W + gx;
+                int out = kNoVote;
+                if (my_cnt >= 0) {
+                    const int best = (int)(my_key >> 10), bestb = 1023 - (int)(my_key & 1023u);
+                    const int max_d = (best > 0) ? (bestb - a.zd) : (int)disp[pix];
+                    // dr_irv_kernel_3: ratio test on the histogram INDEX (Q16)
+                    const bool ok = my_cnt > a.thresh_s && __fdiv_rn((float)(max_d + a.zd), (float)my_cnt) > a.thresh_h;
+                    if (ok) out = max_d;
+                }
+                vote[pix] = out;
             }
         }
     }
